@@ -1,0 +1,304 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a:  out = act(A · Wᵀ + bias) + residual.
+//
+//   A [M,K] bf16 (K contiguous), W [N,K] bf16 (K contiguous, nn.Linear layout), fp32 accumulation.
+//
+//   warp 0      : TMA producer   (one lane) — 128B-swizzled {64 x 128} A tiles and {64 x BN} W tiles
+//   warp 1      : MMA issuer     (one lane) — tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16
+//   warp 2      : TMEM allocator (2 x BN fp32 columns: double-buffered accumulator)
+//   warps 4..11 : epilogue       — tcgen05.ld TMEM->registers, bias / erf-GELU / residual, stores
+//
+// Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue) and the static
+// persistent tile schedule (tile = blockIdx.x + i * gridDim.x, N-blocks fastest so that the CTAs
+// running concurrently share the same A rows in L2 while W stays L2-resident).
+//
+// Replaces: every nn.Linear on Aurora's forward path (see include/aurora_b200.h).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace ab {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kNumEpiWarps = 8;
+constexpr int kNumThreads = 128 + kNumEpiWarps * 32;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStageBytesA = kBlockM * kBlockK * 2;
+  static constexpr int kStageBytesB = BN * kBlockK * 2;
+  static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr uint32_t kTmemCols = 2 * BN;  // two accumulator stages
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + 1024;  // +1024: manual alignment
+  static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols >= 32 && kTmemCols <= 512, "TMEM columns");
+  static_assert((2 * kStages + 4) * 8 + 4 <= kBarrierBytes, "barrier area");
+};
+
+struct GemmArgs {
+  const float* bias;
+  const float* residual;
+  float* out_f32;
+  __nv_bfloat16* out_bf16;
+  int m, n, k;
+  int ldr, ld_f32, ld_bf16;
+  int act;
+  int vec_ok;  // all leading dimensions / pointers allow 16-byte vector access
+};
+
+template <int BN>
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t (&v)[32], int row, int col0) {
+  if (row >= g.m) return;
+  if (g.vec_ok && col0 + 32 <= g.n) {
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    if (g.bias != nullptr) {
+      const float4* b4 = reinterpret_cast<const float4*>(g.bias + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 b = __ldg(b4 + j);
+        f[4 * j + 0] += b.x;
+        f[4 * j + 1] += b.y;
+        f[4 * j + 2] += b.z;
+        f[4 * j + 3] += b.w;
+      }
+    }
+    if (g.act == AB_ACT_GELU_ERF) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+    }
+    if (g.residual != nullptr) {
+      const float4* r4 = reinterpret_cast<const float4*>(g.residual + static_cast<size_t>(row) * g.ldr + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 r = __ldg(r4 + j);
+        f[4 * j + 0] += r.x;
+        f[4 * j + 1] += r.y;
+        f[4 * j + 2] += r.z;
+        f[4 * j + 3] += r.w;
+      }
+    }
+    if (g.out_f32 != nullptr) {
+      float4* o4 = reinterpret_cast<float4*>(g.out_f32 + static_cast<size_t>(row) * g.ld_f32 + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+    }
+    if (g.out_bf16 != nullptr) {
+      uint4* o4 = reinterpret_cast<uint4*>(g.out_bf16 + static_cast<size_t>(row) * g.ld_bf16 + col0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 p;
+        p.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+        p.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+        p.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+        p.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+        o4[j] = p;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      int col = col0 + j;
+      if (col >= g.n) continue;
+      float x = __uint_as_float(v[j]);
+      if (g.bias != nullptr) x += __ldg(g.bias + col);
+      if (g.act == AB_ACT_GELU_ERF) x = gelu_erf(x);
+      if (g.residual != nullptr) x += __ldg(g.residual + static_cast<size_t>(row) * g.ldr + col);
+      if (g.out_f32 != nullptr) g.out_f32[static_cast<size_t>(row) * g.ld_f32 + col] = x;
+      if (g.out_bf16 != nullptr) g.out_bf16[static_cast<size_t>(row) * g.ld_bf16 + col] = __float2bfloat16_rn(x);
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                    const GemmArgs g) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled tiles need 1024-byte alignment.
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kStageBytesA;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;  // warp-uniform
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], kNumEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_n = (g.n + BN - 1) / BN;
+  const int num_m = (g.m + kBlockM - 1) / kBlockM;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (g.k + kBlockK - 1) / kBlockK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * kBlockM;
+        const int n0 = (tile % num_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          tma_load_2d(smem_a + s * Cfg::kStageBytesA, &tmap_a, &full_bar[s], kb * kBlockK, m0);
+          tma_load_2d(smem_b + s * Cfg::kStageBytesB, &tmap_w, &full_bar[s], kb * kBlockK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(kBlockM, BN);
+      uint32_t it = 0, tc = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tc) {
+        const uint32_t as = tc & 1u;
+        const uint32_t aph = (tc >> 1) & 1u;
+        mbar_wait(&tmem_empty_bar[as], aph ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem_a + s * Cfg::kStageBytesA);
+          const uint32_t b_addr = smem_u32(smem_b + s * Cfg::kStageBytesB);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t da = umma_desc_k_sw128(a_addr + k * kUmmaK * 2);
+            const uint64_t db = umma_desc_k_sw128(b_addr + k * kUmmaK * 2);
+            umma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);                           // smem slot free once these MMAs retire
+          if (kb == num_kb - 1) umma_commit(&tmem_full_bar[as]);  // accumulator ready for the epilogue
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue =====
+    const int q = warp & 3;              // TMEM lane quadrant this warp may access
+    const int half = (warp - 4) >> 2;    // column half of the tile
+    uint32_t tc = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tc) {
+      const int m0 = (tile / num_n) * kBlockM;
+      const int n0 = (tile % num_n) * BN;
+      const uint32_t as = tc & 1u;
+      const uint32_t aph = (tc >> 1) & 1u;
+      mbar_wait(&tmem_full_bar[as], aph);
+      tc_fence_after_sync();
+      const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c, v);
+        tmem_ld_wait();
+        epilogue_chunk<BN>(g, v, row, n0 + c);
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN>
+static int launch_gemm(const AbGemm* p, const GemmArgs& args, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap ta, tw;
+  int rc = make_tmap_bf16_2d(&ta, p->a, p->m, p->k, p->lda, kBlockM, kBlockK);
+  if (rc != AB_OK) return rc;
+  rc = make_tmap_bf16_2d(&tw, p->w, p->n, p->k, p->ldw, BN, kBlockK);
+  if (rc != AB_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("ab_gemm_bf16: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+      return AB_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const long long tiles = ceil_div_ll(p->m, kBlockM) * ceil_div_ll(p->n, BN);
+  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  gemm_bf16_tn_kernel<BN><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tw, args);
+  AB_COUNT_LAUNCH(1);
+  AB_CHECK_LAUNCH("ab_gemm_bf16");
+  return AB_OK;
+}
+
+}  // namespace ab
+
+extern "C" int ab_gemm_bf16(const AbGemm* p, void* stream) {
+  using namespace ab;
+  AB_CHECK_ARG(p != nullptr, "ab_gemm_bf16: null descriptor");
+  AB_CHECK_ARG(p->m > 0 && p->n > 0 && p->k > 0, "ab_gemm_bf16: bad shape m=%d n=%d k=%d", p->m, p->n, p->k);
+  AB_CHECK_ARG(p->a != nullptr && p->w != nullptr, "ab_gemm_bf16: null operand");
+  AB_CHECK_ARG(p->out_f32 != nullptr || p->out_bf16 != nullptr, "ab_gemm_bf16: no output requested");
+  AB_CHECK_ARG(p->k % 8 == 0 && p->lda % 8 == 0 && p->ldw % 8 == 0 && p->lda >= p->k && p->ldw >= p->k,
+               "ab_gemm_bf16: K/lda/ldw must be multiples of 8 and ld >= K (k=%d lda=%d ldw=%d)", p->k, p->lda,
+               p->ldw);
+  AB_CHECK_ARG(p->act == AB_ACT_NONE || p->act == AB_ACT_GELU_ERF, "ab_gemm_bf16: unknown activation %d", p->act);
+  AB_CHECK_ARG(p->out_f32 == nullptr || p->ld_f32 >= p->n, "ab_gemm_bf16: ld_f32 < n");
+  AB_CHECK_ARG(p->out_bf16 == nullptr || p->ld_bf16 >= p->n, "ab_gemm_bf16: ld_bf16 < n");
+  AB_CHECK_ARG(p->residual == nullptr || p->ldr >= p->n, "ab_gemm_bf16: ldr < n");
+
+  GemmArgs a;
+  a.bias = p->bias;
+  a.residual = p->residual;
+  a.out_f32 = p->out_f32;
+  a.out_bf16 = reinterpret_cast<__nv_bfloat16*>(p->out_bf16);
+  a.m = p->m;
+  a.n = p->n;
+  a.k = p->k;
+  a.ldr = p->ldr;
+  a.ld_f32 = p->ld_f32;
+  a.ld_bf16 = p->ld_bf16;
+  a.act = p->act;
+  auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  a.vec_ok = al16(p->bias) && al16(p->residual) && al16(p->out_f32) && al16(p->out_bf16) &&
+             (p->residual == nullptr || p->ldr % 4 == 0) && (p->out_f32 == nullptr || p->ld_f32 % 4 == 0) &&
+             (p->out_bf16 == nullptr || p->ld_bf16 % 8 == 0);
+
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (p->n > 128) return launch_gemm<256>(p, a, s);
+  if (p->n > 64) return launch_gemm<128>(p, a, s);
+  return launch_gemm<64>(p, a, s);
+}

@@ -1,0 +1,86 @@
+"""tcgen05 GEMM (ab_gemm_bf16) against a plain PyTorch fp32 reference of the same op."""
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, w, bias, residual, act):
+    y = a.float() @ w.float().t()
+    if bias is not None:
+        y = y + bias
+    if act:
+        y = torch.nn.functional.gelu(y)
+    if residual is not None:
+        y = y + residual
+    return y
+
+
+SHAPES = [
+    # (M, N, K)
+    (128, 256, 64),
+    (128, 256, 512),
+    (256, 512, 128),
+    (300, 256, 192),     # M tail
+    (1000, 1536, 512),   # qkv-like
+    (777, 80, 1024),     # decoder heads: N tail inside a 128-wide tile
+    (64, 64, 256),       # tiny
+    (129, 520, 72),      # M, N and K tails (K % 64 != 0)
+    (4096, 2048, 512),   # fc1 stage-1-like, many tiles per CTA
+    (2048, 512, 2048),   # fc2-like, long K
+    (5, 16, 8),          # minimum sizes
+]
+
+
+@pytest.mark.parametrize("m,n,k", SHAPES)
+@pytest.mark.parametrize("mode", ["plain_bf16", "bias_gelu_bf16", "bias_res_f32_dual"])
+def test_gemm_matches_fp32_reference(m, n, k, mode):
+    from aurora_b200 import cabi
+
+    torch.manual_seed(m * 31 + n * 7 + k)
+    dev = "cuda"
+    a = torch.randn(m, k, device=dev).to(torch.bfloat16)
+    w = (torch.randn(n, k, device=dev) / k**0.5).to(torch.bfloat16)
+    bias = torch.randn(n, device=dev) if mode != "plain_bf16" else None
+    residual = torch.randn(m, n, device=dev) if mode == "bias_res_f32_dual" else None
+    act = cabi.AB_ACT_GELU_ERF if mode == "bias_gelu_bf16" else cabi.AB_ACT_NONE
+    out_bf16 = torch.full((m, n), float("nan"), device=dev, dtype=torch.bfloat16)
+    out_f32 = torch.full((m, n), float("nan"), device=dev) if mode == "bias_res_f32_dual" else None
+
+    cabi.gemm(a, w, bias=bias, residual=residual, out_f32=out_f32, out_bf16=out_bf16, act=act)
+    torch.cuda.synchronize()
+
+    ref = _ref(a, w, bias, residual, act)
+    # fp32 accumulation of bf16 products: only the output rounding differs from the fp32 reference.
+    if out_f32 is not None:
+        torch.testing.assert_close(out_f32, ref, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(out_bf16.float(), ref, rtol=1e-2, atol=1e-2)
+
+
+def test_gemm_strided_views():
+    """Leading dimensions larger than the logical width (writes into a slice of a wider buffer)."""
+    from aurora_b200 import cabi
+
+    torch.manual_seed(0)
+    m, n, k = 384, 256, 128
+    a_full = torch.randn(m, 2 * k, device="cuda").to(torch.bfloat16)
+    a = a_full[:, k:]
+    w = (torch.randn(n, k, device="cuda") / k**0.5).to(torch.bfloat16)
+    out_full = torch.zeros(m, 2 * n, device="cuda", dtype=torch.bfloat16)
+    out = out_full[:, n:]
+    cabi.gemm(a, w, out_bf16=out)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t()
+    torch.testing.assert_close(out.float(), ref, rtol=1e-2, atol=1e-2)
+    assert out_full[:, :n].abs().max().item() == 0.0
+
+
+def test_gemm_rejects_bad_arguments():
+    from aurora_b200 import cabi
+
+    a = torch.zeros(16, 12, device="cuda", dtype=torch.bfloat16)  # K % 8 != 0
+    w = torch.zeros(16, 12, device="cuda", dtype=torch.bfloat16)
+    out = torch.zeros(16, 16, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(cabi.AbError):
+        cabi.gemm(a, w, out_bf16=out)
