@@ -1,0 +1,176 @@
+"""``Batch`` and ``Metadata``: the data model at the boundary of ``Aurora.forward``.
+
+Same field names, shapes, validation and error behaviour as the reference (`aurora/batch.py:24-190`),
+restricted to the methods on the forward path: ``normalise`` / ``unnormalise`` / ``crop`` / ``to`` /
+``type``.  File I/O and re-gridding (`aurora/batch.py:192-362`) are outside the accelerated path and
+not provided.  On the GPU path normalisation is fused into the patch-embedding loader and
+un-normalisation into the head's store; the methods here exist for API parity and for callers that
+want the tensors themselves.
+"""
+
+from __future__ import annotations
+
+import dataclasses
+from datetime import datetime
+from typing import Callable, Optional
+
+import torch
+
+from aurora_b200.stats import atmos_stats_of, surf_stats_of
+
+__all__ = ["Metadata", "Batch"]
+
+
+@dataclasses.dataclass
+class Metadata:
+    """Metadata of a batch (`aurora/batch.py:24-68`).
+
+    Args:
+        lat: Latitudes, strictly decreasing vector (or matrix), in [-90, 90].
+        lon: Longitudes, strictly increasing vector (or matrix), in [0, 360).
+        time: One ``datetime`` per batch element.
+        atmos_levels: Pressure levels in hPa.
+        rollout_step: 0 for analysis data; the model increments it for every prediction.
+    """
+
+    lat: torch.Tensor
+    lon: torch.Tensor
+    time: tuple[datetime, ...]
+    atmos_levels: tuple[int | float, ...]
+    rollout_step: int = 0
+
+    def __post_init__(self) -> None:
+        if not (torch.all(self.lat <= 90) and torch.all(self.lat >= -90)):
+            raise ValueError("Latitudes must be in the range [-90, 90].")
+        if not (torch.all(self.lon >= 0) and torch.all(self.lon < 360)):
+            raise ValueError("Longitudes must be in the range [0, 360).")
+        if self.lat.dim() == self.lon.dim() == 1:
+            if not torch.all(self.lat[1:] - self.lat[:-1] < 0):
+                raise ValueError("Latitudes must be strictly decreasing.")
+            if not torch.all(self.lon[1:] - self.lon[:-1] > 0):
+                raise ValueError("Longitudes must be strictly increasing.")
+        elif self.lat.dim() == self.lon.dim() == 2:
+            if not torch.all(self.lat[1:, :] - self.lat[:-1, :]):
+                raise ValueError("Latitudes must be strictly decreasing along every column.")
+            if not torch.all(self.lon[:, 1:] - self.lon[:, :-1] > 0):
+                raise ValueError("Longitudes must be strictly increasing along every row.")
+        else:
+            raise ValueError("The latitudes and longitudes must either both be vectors or both be matrices.")
+
+
+def _affine(x: torch.Tensor, loc, scale, inverse: bool) -> torch.Tensor:
+    return x * scale + loc if inverse else (x - loc) / scale
+
+
+def _norm_surf(x, name, stats, inverse):
+    loc, scale = surf_stats_of(name, stats)
+    return _affine(x, loc, scale, inverse)
+
+
+def _norm_atmos(x, name, levels, inverse):
+    locs, scs = atmos_stats_of(name, levels)
+    loc = torch.tensor(locs, dtype=x.dtype, device=x.device)[..., None, None]
+    scale = torch.tensor(scs, dtype=x.dtype, device=x.device)[..., None, None]
+    return _affine(x, loc, scale, inverse)
+
+
+@dataclasses.dataclass
+class Batch:
+    """A batch of data (`aurora/batch.py:72-190`).
+
+    Args:
+        surf_vars: Surface-level variables, each ``(b, t, h, w)``.
+        static_vars: Static variables, each ``(h, w)``.
+        atmos_vars: Atmospheric variables, each ``(b, t, c, h, w)``.
+        metadata: Associated :class:`Metadata`.
+    """
+
+    surf_vars: dict[str, torch.Tensor]
+    static_vars: dict[str, torch.Tensor]
+    atmos_vars: dict[str, torch.Tensor]
+    metadata: Metadata
+
+    @property
+    def spatial_shape(self) -> tuple[int, int]:
+        return tuple(next(iter(self.surf_vars.values())).shape[-2:])
+
+    def _map_vars(self, fs, fst, fa) -> "Batch":
+        return Batch(
+            surf_vars={k: fs(k, v) for k, v in self.surf_vars.items()},
+            static_vars={k: fst(k, v) for k, v in self.static_vars.items()},
+            atmos_vars={k: fa(k, v) for k, v in self.atmos_vars.items()},
+            metadata=self.metadata,
+        )
+
+    def normalise(self, surf_stats: Optional[dict[str, tuple[float, float]]] = None) -> "Batch":
+        """``(x - location) / scale`` per variable (and per level for atmospheric variables)."""
+        lv = self.metadata.atmos_levels
+        return self._map_vars(
+            lambda k, v: _norm_surf(v, k, surf_stats, False),
+            lambda k, v: _norm_surf(v, k, surf_stats, False),
+            lambda k, v: _norm_atmos(v, k, lv, False),
+        )
+
+    def unnormalise(self, surf_stats: Optional[dict[str, tuple[float, float]]] = None) -> "Batch":
+        """Inverse of :meth:`normalise`."""
+        lv = self.metadata.atmos_levels
+        return self._map_vars(
+            lambda k, v: _norm_surf(v, k, surf_stats, True),
+            lambda k, v: _norm_surf(v, k, surf_stats, True),
+            lambda k, v: _norm_atmos(v, k, lv, True),
+        )
+
+    def crop(self, patch_size: int) -> "Batch":
+        """Drop the last latitude row when ``h % patch_size == 1`` (e.g. 721 -> 720)."""
+        h, w = self.spatial_shape
+        if w % patch_size != 0:
+            raise ValueError("Width of the data must be a multiple of the patch size.")
+        if h % patch_size == 0:
+            return self
+        if h % patch_size == 1:
+            cut = lambda _k, v: v[..., :-1, :]  # noqa: E731
+            out = self._map_vars(cut, cut, cut)
+            out.metadata = Metadata(
+                lat=self.metadata.lat[:-1],
+                lon=self.metadata.lon,
+                atmos_levels=self.metadata.atmos_levels,
+                time=self.metadata.time,
+                rollout_step=self.metadata.rollout_step,
+            )
+            return out
+        raise ValueError(
+            f"There can at most be one latitude too many, but there are {h % patch_size} too many."
+        )
+
+    def _fmap(self, f: Callable[[torch.Tensor], torch.Tensor]) -> "Batch":
+        return Batch(
+            surf_vars={k: f(v) for k, v in self.surf_vars.items()},
+            static_vars={k: f(v) for k, v in self.static_vars.items()},
+            atmos_vars={k: f(v) for k, v in self.atmos_vars.items()},
+            metadata=Metadata(
+                lat=f(self.metadata.lat),
+                lon=f(self.metadata.lon),
+                atmos_levels=self.metadata.atmos_levels,
+                time=self.metadata.time,
+                rollout_step=self.metadata.rollout_step,
+            ),
+        )
+
+    def to(self, device: str | torch.device) -> "Batch":
+        """Move every tensor (incl. lat/lon) to ``device``."""
+        return self._fmap(lambda x: x.to(device))
+
+    def type(self, t) -> "Batch":
+        """Convert every tensor (incl. lat/lon) to dtype ``t``."""
+        return self._fmap(lambda x: x.type(t))
+
+    # -- outside the accelerated path ---------------------------------------------------------
+    def regrid(self, res: float) -> "Batch":  # pragma: no cover
+        raise NotImplementedError("Batch.regrid (aurora/batch.py:192) is host-side I/O, not part of aurora_b200")
+
+    def to_netcdf(self, path) -> None:  # pragma: no cover
+        raise NotImplementedError("netCDF I/O (aurora/batch.py:224) is not part of aurora_b200")
+
+    @classmethod
+    def from_netcdf(cls, path) -> "Batch":  # pragma: no cover
+        raise NotImplementedError("netCDF I/O (aurora/batch.py:260) is not part of aurora_b200")

@@ -1,0 +1,156 @@
+"""Deterministic, platform-independent test fixtures (numpy PCG64): model configurations, parameters
+with the reference's zero-initialised tensors re-drawn (otherwise every Swin block is an identity,
+SURVEY.md F3) and physically scaled synthetic batches (`loc + scale * N(0,1)`).
+
+Used both by tests/golden/make_golden.py (in the build container, next to the imported reference)
+and by the tests themselves (here and on the GPU box), so both sides see identical bits.
+"""
+
+from __future__ import annotations
+
+import dataclasses
+import math
+from datetime import datetime, timedelta
+
+import numpy as np
+import torch
+
+from aurora_b200.batch import Batch, Metadata
+from aurora_b200.spec import ModelConfig, param_specs
+from aurora_b200.stats import atmos_stats_of, surf_stats_of
+
+LEVELS13 = (50, 100, 150, 200, 250, 300, 400, 500, 600, 700, 850, 925, 1000)
+LEVELS4 = (100, 250, 500, 850)
+
+AIR_SURF = ("2t", "10u", "10v", "msl", "pm1", "pm2p5", "pm10", "tcco", "tc_no", "tcno2", "gtco3", "tcso2")
+AIR_STATIC = ("lsm", "z", "slt", "static_ammonia", "static_ammonia_log", "static_co", "static_co_log",
+              "static_nox", "static_nox_log", "static_so2", "static_so2_log")
+AIR_ATMOS = ("z", "u", "v", "t", "q", "co", "no", "no2", "go3", "so2")
+AIR_DIFF = ("pm1", "pm2p5", "pm10", "co", "tcco", "no", "tc_no", "no2", "tcno2", "so2", "tcso2", "go3", "gtco3")
+
+CONFIGS: dict[str, ModelConfig] = {
+    # 3-stage U-Net, head_dim 64 in every Swin stage like all presets; tiny widths.
+    "tiny": ModelConfig(
+        embed_dim=128, num_heads=4, encoder_depths=(2, 2, 2), encoder_num_heads=(2, 4, 8),
+        decoder_depths=(2, 2, 2), decoder_num_heads=(8, 4, 2), use_lora=False,
+    ),
+    "tiny_lora": ModelConfig(
+        embed_dim=128, num_heads=4, encoder_depths=(2, 2, 2), encoder_num_heads=(2, 4, 8),
+        decoder_depths=(2, 2, 2), decoder_num_heads=(8, 4, 2), use_lora=True, lora_mode="single",
+    ),
+    "tiny_lora_all": ModelConfig(
+        embed_dim=128, num_heads=4, encoder_depths=(2, 2, 2), encoder_num_heads=(2, 4, 8),
+        decoder_depths=(2, 2, 2), decoder_num_heads=(8, 4, 2), use_lora=True, lora_mode="all", lora_steps=3,
+    ),
+    "tiny_12h_stab": ModelConfig(
+        embed_dim=128, num_heads=4, encoder_depths=(2, 2, 2), encoder_num_heads=(2, 4, 8),
+        decoder_depths=(2, 2, 2), decoder_num_heads=(8, 4, 2), use_lora=True, lora_mode="from_second",
+        timestep=timedelta(hours=12), stabilise_level_agg=True,
+    ),
+    "tiny_air": ModelConfig(
+        surf_vars=AIR_SURF, static_vars=AIR_STATIC, atmos_vars=AIR_ATMOS, patch_size=3,
+        timestep=timedelta(hours=12), level_condition=LEVELS13, dynamic_vars=True, atmos_static_vars=True,
+        separate_perceiver=("co", "no", "no2", "go3", "so2"), modulation_heads=AIR_DIFF,
+        positive_surf_vars=AIR_SURF[4:], positive_atmos_vars=AIR_ATMOS[5:], simulate_indexing_bug=True,
+        embed_dim=128, num_heads=4, encoder_depths=(2, 2, 2), encoder_num_heads=(2, 4, 8),
+        decoder_depths=(2, 2, 2), decoder_num_heads=(8, 4, 2), use_lora=True,
+    ),
+    # AuroraSmallPretrained (aurora.py:568-598)
+    "small": ModelConfig(
+        embed_dim=256, num_heads=8, encoder_depths=(2, 6, 2), encoder_num_heads=(4, 8, 16),
+        decoder_depths=(2, 6, 2), decoder_num_heads=(16, 8, 4), use_lora=False,
+    ),
+    # Aurora / AuroraPretrained (1.3 B) and AuroraHighRes
+    "aurora": ModelConfig(),
+    "pretrained": ModelConfig(use_lora=False),
+    "highres": ModelConfig(patch_size=10, encoder_depths=(6, 8, 8), decoder_depths=(8, 8, 6)),
+}
+
+
+def air_extra_specs(cfg: ModelConfig):
+    """AuroraAirPollution's feature combiners (aurora.py:716-724)."""
+    out = []
+    for grp, names in (("surf_feature_combiner", cfg.positive_surf_vars), ("atmos_feature_combiner", cfg.positive_atmos_vars)):
+        for v in names:
+            out.append((f"{grp}.{v}.weight", (1, 2), "half"))
+            out.append((f"{grp}.{v}.bias", (1,), "zeros"))
+    return out
+
+
+def make_state_dict(cfg: ModelConfig, seed: int = 0, extra=(), zero_init_std: float = 0.1) -> dict[str, torch.Tensor]:
+    """Parameters drawn from numpy PCG64.  Linear weights ~ N(0, 0.02) (clipped at 2 sigma like the
+    reference's trunc_normal_), patch-embedding / LoRA-A uniform in the Kaiming bound; the reference's
+    zero-initialised tensors (adaLN modulation, LoRA-B, biases) ~ N(0, zero_init_std) or small noise so
+    that every block contributes."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    sd = {}
+    for key, shape, kind in list(param_specs(cfg)) + list(extra):
+        n = int(np.prod(shape))
+        if kind in ("linear_w", "latent"):
+            a = np.clip(rng.standard_normal(n), -2.0, 2.0) * 0.02
+        elif kind in ("patch_w", "lora_a"):
+            a = rng.uniform(-1.0, 1.0, n) / math.sqrt(np.prod(shape[1:]))
+        elif kind == "patch_b":
+            a = rng.uniform(-1.0, 1.0, n) / math.sqrt(cfg.max_history_size * cfg.patch_size**2)
+        elif kind == "ones":
+            a = 1.0 + 0.1 * rng.standard_normal(n)
+        elif kind == "half":
+            a = 0.5 + 0.05 * rng.standard_normal(n)
+        elif kind == "zeros":
+            if "ln_modulation" in key:
+                a = zero_init_std * rng.standard_normal(n)
+            elif "lora_B" in key:
+                a = 0.02 * rng.standard_normal(n)
+            else:
+                a = 0.02 * rng.standard_normal(n)
+        else:  # pragma: no cover
+            raise ValueError(kind)
+        sd[key] = torch.from_numpy(a.reshape(shape).astype(np.float32))
+    return sd
+
+
+def make_batch(cfg: ModelConfig, h: int, w: int, levels=LEVELS13, b: int = 1, t: int = 2, seed: int = 0,
+               rollout_step: int = 0, time0: datetime = datetime(2020, 6, 1, 12, 0)) -> Batch:
+    """ERA5-shaped synthetic batch with physical magnitudes: `loc + scale * N(0,1)` per variable and
+    level.  `lat = linspace(90,-90,h)`, `lon = linspace(0,360,w+1)[:-1]` (README / finetune.py)."""
+    rng = np.random.Generator(np.random.PCG64(1000 + seed))
+
+    def field(shape, loc, scale):
+        return torch.from_numpy((loc + scale * rng.standard_normal(shape)).astype(np.float32))
+
+    surf = {}
+    for k in cfg.surf_vars:
+        loc, sc = surf_stats_of(k)
+        surf[k] = field((b, t, h, w), loc, sc)
+    static = {}
+    for k in cfg.static_vars:
+        loc, sc = surf_stats_of(k)
+        static[k] = field((h, w), loc, sc)
+    atmos = {}
+    for k in cfg.atmos_vars:
+        locs, scs = atmos_stats_of(k, levels)
+        loc = np.asarray(locs)[None, None, :, None, None]
+        sc = np.asarray(scs)[None, None, :, None, None]
+        atmos[k] = field((b, t, len(levels), h, w), loc, sc)
+    # Positive variables: keep the physical sign so the log-transform path (air pollution) is exercised
+    # on both sides of its clamp.
+    meta = Metadata(
+        lat=torch.linspace(90, -90, h),
+        lon=torch.linspace(0, 360, w + 1)[:-1],
+        time=tuple(time0 + timedelta(hours=6 * i) for i in range(b)),
+        atmos_levels=tuple(levels),
+        rollout_step=rollout_step,
+    )
+    return Batch(surf, static, atmos, meta)
+
+
+def reference_kwargs(cfg: ModelConfig) -> dict:
+    """Constructor keyword arguments for the reference's `Aurora(...)` equivalent to `cfg`."""
+    kw = dataclasses.asdict(cfg)
+    kw["surf_stats"] = dict(cfg.surf_stats) if cfg.surf_stats else None
+    return kw
+
+
+def rel_mean_abs(out: torch.Tensor, ref: torch.Tensor) -> float:
+    """The reference's own acceptance metric: mean|out - ref| / mean|ref| (tests/test_model.py:45-61)."""
+    return float((out.double() - ref.double()).abs().mean() / ref.double().abs().mean().clamp_min(1e-30))
