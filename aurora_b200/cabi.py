@@ -14,7 +14,11 @@ import torch
 
 from aurora_b200 import _build
 
-__all__ = ["lib", "AbError", "check", "ptr", "stream_ptr", "gemm", "launch_count"]
+__all__ = [
+    "lib", "AbError", "check", "ptr", "stream_ptr", "launch_count", "gemm", "window_attention", "window_geometry",
+    "window_index_map", "ln_mod_residual", "patch_merge_ln", "patch_split_ln", "perceiver_attention",
+    "linear_small", "patchify", "unpatchify", "AbFieldIn", "AbFieldOut",
+]
 
 AB_ACT_NONE = 0
 AB_ACT_GELU_ERF = 1
@@ -72,7 +76,19 @@ EXPORTS = [
     "ab_last_error",
     "ab_launch_count",
     "ab_gemm_bf16",
+    "ab_window_attention",
+    "ab_window_geometry",
+    "ab_window_index_map",
+    "ab_ln_mod_residual",
+    "ab_patch_merge_ln",
+    "ab_patch_split_ln",
+    "ab_perceiver_attention",
+    "ab_linear_small_f32",
+    "ab_patchify",
+    "ab_unpatchify",
 ]
+AB_MAX_FIELDS = 40
+AB_IN_PLAIN, AB_IN_CLAMP_MIN0, AB_IN_CLAMP_LOG_COMBINE = 0, 1, 2
 
 
 def check(status: int, what: str = "") -> None:
@@ -139,3 +155,202 @@ def gemm(
         g.ld_bf16 = _ld(out_bf16)
     g.act = act
     check(lib().ab_gemm_bf16(C.byref(g), C.c_void_p(stream_ptr())), "ab_gemm_bf16")
+
+
+class AbWindowAttention(C.Structure):
+    _fields_ = [
+        ("qkv", C.c_void_p),
+        ("pad_qkv", C.c_void_p),
+        ("out", C.c_void_p),
+        ("bias", C.c_void_p),
+        ("batch", C.c_int32),
+        ("res", C.c_int32 * 3),
+        ("window", C.c_int32 * 3),
+        ("shift", C.c_int32 * 3),
+        ("num_heads", C.c_int32),
+        ("head_dim", C.c_int32),
+        ("warped", C.c_int32),
+    ]
+
+
+class AbLnModResidual(C.Structure):
+    _fields_ = [
+        ("y", C.c_void_p),
+        ("scale", C.c_void_p),
+        ("shift", C.c_void_p),
+        ("residual", C.c_void_p),
+        ("add_rows", C.c_void_p),
+        ("out_f32", C.c_void_p),
+        ("out_bf16", C.c_void_p),
+        ("rows", C.c_int64),
+        ("res_div", C.c_int64),
+        ("res_mod", C.c_int64),
+        ("add_mod", C.c_int64),
+        ("dim", C.c_int32),
+        ("ld_y", C.c_int32),
+        ("ld_res", C.c_int32),
+        ("ld_f32", C.c_int32),
+        ("ld_bf16", C.c_int32),
+        ("eps", C.c_float),
+    ]
+
+
+class AbFieldIn(C.Structure):
+    _fields_ = [
+        ("ptr", C.c_void_p),
+        ("stride_t", C.c_int64),
+        ("loc", C.c_float),
+        ("scale", C.c_float),
+        ("const_value", C.c_float),
+        ("transform", C.c_int32),
+        ("w0", C.c_float),
+        ("w1", C.c_float),
+        ("wb", C.c_float),
+    ]
+
+
+class AbFieldOut(C.Structure):
+    _fields_ = [
+        ("ptr", C.c_void_p),
+        ("prev", C.c_void_p),
+        ("loc", C.c_float),
+        ("scale", C.c_float),
+        ("col", C.c_int32),
+        ("mod_col", C.c_int32),
+        ("clamp_min0", C.c_int32),
+        ("clamp_max1", C.c_int32),
+    ]
+
+
+def _i3(v):
+    return (C.c_int32 * 3)(*[int(x) for x in v])
+
+
+def _s():
+    return C.c_void_p(stream_ptr())
+
+
+def window_geometry(res, window, shift) -> tuple[int, int, bool]:
+    """(windows per batch element, tokens per clamped window, mask applies) — host only."""
+    nw, nt, sh = C.c_int32(), C.c_int32(), C.c_int32()
+    check(lib().ab_window_geometry(_i3(res), _i3(window), _i3(shift), C.byref(nw), C.byref(nt), C.byref(sh)),
+          "ab_window_geometry")
+    return nw.value, nt.value, bool(sh.value)
+
+
+def window_index_map(res, window, shift, warped: bool = True, device="cuda"):
+    """Materialise the in-kernel gather map / group ids (test hook)."""
+    nw, nt, _ = window_geometry(res, window, shift)
+    idx = torch.empty(nw * nt, dtype=torch.int32, device=device)
+    grp = torch.empty(nw * nt, dtype=torch.uint8, device=device)
+    check(lib().ab_window_index_map(_i3(res), _i3(window), _i3(shift), C.c_int32(int(warped)),
+                                    C.c_void_p(ptr(idx)), C.c_void_p(ptr(grp)), _s()), "ab_window_index_map")
+    return idx.view(nw, nt), grp.view(nw, nt)
+
+
+def window_attention(qkv: torch.Tensor, out: torch.Tensor, *, batch: int, res, window, shift, num_heads: int,
+                     pad_qkv: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+                     warped: bool = True) -> None:
+    assert qkv.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and qkv.is_contiguous() and out.is_contiguous()
+    d = num_heads * 64
+    tokens = batch * res[0] * res[1] * res[2]
+    assert qkv.shape == (tokens, 3 * d) and out.shape == (tokens, d), (qkv.shape, out.shape, tokens, d)
+    a = AbWindowAttention()
+    a.qkv, a.out = ptr(qkv), ptr(out)
+    if pad_qkv is not None:
+        assert pad_qkv.dtype == torch.bfloat16 and pad_qkv.numel() == 3 * d and pad_qkv.is_contiguous()
+    a.pad_qkv = ptr(pad_qkv)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous()
+    a.bias = ptr(bias)
+    a.batch = batch
+    a.res, a.window, a.shift = _i3(res), _i3(window), _i3(shift)
+    a.num_heads, a.head_dim, a.warped = num_heads, 64, int(warped)
+    check(lib().ab_window_attention(C.byref(a), _s()), "ab_window_attention")
+
+
+def ln_mod_residual(y: torch.Tensor, *, scale=None, shift=None, residual=None, add_rows=None, out_f32=None,
+                    out_bf16=None, eps: float = 1e-5, res_div: int = 1, res_mod: int = 0) -> None:
+    assert y.dtype == torch.bfloat16 and y.dim() == 2
+    rows, dim = y.shape
+    a = AbLnModResidual()
+    a.y = ptr(y)
+    a.ld_y = _ld(y)
+    for t in (scale, shift):
+        assert t is None or (t.dtype == torch.float32 and t.numel() == dim and t.is_contiguous())
+    a.scale, a.shift = ptr(scale), ptr(shift)
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.shape[1] == dim
+        a.residual, a.ld_res = ptr(residual), _ld(residual)
+        if res_mod == 0:
+            assert residual.shape[0] == rows
+        else:
+            assert residual.shape[0] >= res_mod
+    if add_rows is not None:
+        assert add_rows.dtype == torch.float32 and add_rows.shape[1] == dim and add_rows.is_contiguous()
+        a.add_rows, a.add_mod = ptr(add_rows), add_rows.shape[0]
+    if out_f32 is not None:
+        assert out_f32.dtype == torch.float32 and out_f32.shape == (rows, dim)
+        a.out_f32, a.ld_f32 = ptr(out_f32), _ld(out_f32)
+    if out_bf16 is not None:
+        assert out_bf16.dtype == torch.bfloat16 and out_bf16.shape == (rows, dim)
+        a.out_bf16, a.ld_bf16 = ptr(out_bf16), _ld(out_bf16)
+    a.rows, a.dim, a.eps = rows, dim, eps
+    a.res_div, a.res_mod = res_div, res_mod
+    check(lib().ab_ln_mod_residual(C.byref(a), _s()), "ab_ln_mod_residual")
+
+
+def patch_merge_ln(x: torch.Tensor, gamma, beta, out: torch.Tensor, *, batch, c, h, w, d, eps=1e-5) -> None:
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.numel() == batch * c * h * w * d
+    assert out.dtype == torch.bfloat16 and out.is_contiguous()
+    assert out.numel() == batch * c * ((h + 1) // 2) * ((w + 1) // 2) * 4 * d
+    check(lib().ab_patch_merge_ln(C.c_void_p(ptr(x)), C.c_void_p(ptr(gamma)), C.c_void_p(ptr(beta)),
+                                  C.c_void_p(ptr(out)), batch, c, h, w, d, C.c_float(eps), _s()), "ab_patch_merge_ln")
+
+
+def patch_split_ln(y: torch.Tensor, gamma, beta, out: torch.Tensor, *, batch, c, h, w, d, crop_h, crop_w,
+                   eps=1e-5) -> None:
+    assert y.dtype == torch.bfloat16 and y.is_contiguous() and y.numel() == batch * c * h * w * 2 * d
+    assert out.dtype == torch.bfloat16 and out.is_contiguous()
+    assert out.numel() == batch * c * (2 * h - crop_h) * (2 * w - crop_w) * (d // 2)
+    check(lib().ab_patch_split_ln(C.c_void_p(ptr(y)), C.c_void_p(ptr(gamma)), C.c_void_p(ptr(beta)),
+                                  C.c_void_p(ptr(out)), batch, c, h, w, d, crop_h, crop_w, C.c_float(eps), _s()),
+          "ab_patch_split_ln")
+
+
+def perceiver_attention(q: torch.Tensor, kv: torch.Tensor, out: torch.Tensor, *, nloc: int, num_heads: int,
+                        head_dim: int) -> None:
+    assert q.dtype == torch.float32 and q.is_contiguous() and q.dim() == 2
+    lq, d = q.shape
+    assert d == num_heads * head_dim
+    assert kv.dtype == torch.bfloat16 and kv.dim() == 2 and kv.shape[1] == 2 * d and kv.shape[0] % nloc == 0
+    lk = kv.shape[0] // nloc
+    assert out.dtype == torch.bfloat16 and out.shape == (lq * nloc, d)
+    check(lib().ab_perceiver_attention(C.c_void_p(ptr(q)), C.c_void_p(ptr(kv)), C.c_void_p(ptr(out)),
+                                       C.c_int64(nloc), lq, lk, num_heads, head_dim, _ld(kv), _ld(out), _s()),
+          "ab_perceiver_attention")
+
+
+def linear_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, silu_in=False,
+                 silu_out=False) -> torch.Tensor:
+    assert x.dtype == torch.float32 and w.dtype == torch.float32 and x.is_contiguous() and w.is_contiguous()
+    rows, k = x.shape
+    n, k2 = w.shape
+    assert k == k2
+    y = torch.empty(rows, n, dtype=torch.float32, device=x.device)
+    check(lib().ab_linear_small_f32(C.c_void_p(ptr(x)), C.c_void_p(ptr(w)), C.c_void_p(ptr(bias)),
+                                    C.c_void_p(ptr(y)), rows, n, k, int(silu_in), int(silu_out), _s()),
+          "ab_linear_small_f32")
+    return y
+
+
+def patchify(fields: list, t_hist: int, h: int, w: int, p: int, out: torch.Tensor) -> None:
+    assert out.dtype == torch.bfloat16 and out.dim() == 2 and out.shape[0] == (h // p) * (w // p)
+    arr = (AbFieldIn * len(fields))(*fields)
+    check(lib().ab_patchify(arr, len(fields), t_hist, h, w, p, C.c_void_p(ptr(out)), _ld(out), _s()), "ab_patchify")
+
+
+def unpatchify(fields: list, y: torch.Tensor, h: int, w: int, p: int) -> None:
+    assert y.dtype == torch.float32 and y.dim() == 2 and y.shape[0] == (h // p) * (w // p)
+    arr = (AbFieldOut * len(fields))(*fields)
+    check(lib().ab_unpatchify(arr, len(fields), C.c_void_p(ptr(y)), _ld(y), h, w, p, _s()), "ab_unpatchify")

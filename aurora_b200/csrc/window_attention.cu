@@ -1,0 +1,349 @@
+// Windowed multi-head self-attention over the FLAT token stream (aurora/model/swin3d.py:136-171 with the
+// partition / shift / mask logic of :470-503 and :303-360 folded into addressing).
+//
+//   qkv  : bf16 [B*L, 3*D]   row = token of the (C,H,W) grid, columns = [q | k | v], head-major, d = 64
+//   out  : bf16 [B*L, D]     merged heads, written back at the SOURCE token (reverse + crop + un-roll)
+//
+// One CTA per (batch, window, head), nine warps; warp w owns query rows [16w, 16w+16).
+//   1. cp.async gather of the window's q/k/v rows (128 B each) into XOR-swizzled shared memory; the
+//      cyclic shift, the zero padding and the window partition are index arithmetic
+//      (window_index.cuh), zero-padded tokens read `pad_qkv` (= the projection bias: x = 0 there);
+//   2. S = Q K^T on mma.sync m16n8k16 (bf16 in, fp32 out), 48 keys at a time with an online softmax;
+//      scale 1/sqrt(64); the shifted-window mask (0 / -100) is generated in registers from one byte
+//      of group id per token; an optional dense additive bias [heads, N, N] can be added too;
+//   3. O += P V, normalise, stage through shared memory, 128-byte coalesced scatter to the source rows.
+//
+// Bound: HBM (reads 3D, writes D bf16 per token: arithmetic intensity ~72 FLOP/B).
+#include "common.h"
+#include "ptx.cuh"
+#include "window_index.cuh"
+
+namespace ab {
+
+constexpr int kHeadDim = 64;
+constexpr int kMaxTok = 144;
+constexpr int kAttnWarps = 9;
+constexpr int kAttnThreads = kAttnWarps * 32;
+constexpr int kKeyBlock = 48;
+constexpr int kRowBytes = kHeadDim * 2;  // 128
+
+struct AttnArgs {
+  const __nv_bfloat16* qkv;
+  const __nv_bfloat16* pad_qkv;
+  __nv_bfloat16* out;
+  const float* bias;
+  WinGeom g;
+  int batch, num_heads, dim;
+  long long tokens_per_batch;
+};
+
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                              uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// Byte offset of 16-byte chunk `chunk` (0..7) of row `row` in a [rows][128 B] XOR-swizzled tile.
+__device__ __forceinline__ uint32_t swz(int row, int chunk) {
+  return static_cast<uint32_t>(row * kRowBytes + ((chunk ^ (row & 7)) << 4));
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 2) window_attention_kernel(const AttnArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const WinGeom& g = a.g;
+  const int ntok = g.ntok;
+  const int npad = (ntok + 15) & ~15;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + npad * kRowBytes;
+  uint8_t* sV = sK + npad * kRowBytes;
+  int* sSrc = reinterpret_cast<int*>(sV + npad * kRowBytes);
+  uint8_t* sGrp = reinterpret_cast<uint8_t*>(sSrc + npad);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  int item = blockIdx.x;
+  const int head = item % a.num_heads;
+  item /= a.num_heads;
+  const int win = item % g.nwindows;
+  const int b = item / g.nwindows;
+  const long long row_base = static_cast<long long>(b) * a.tokens_per_batch;
+  const int ld = 3 * a.dim;
+
+  // ---- 1. index map + gather -------------------------------------------------------------------
+  for (int t = tid; t < npad; t += kAttnThreads) {
+    int grp = kPadGroup;
+    int src = -2;  // rows in [ntok, npad): not part of the window at all
+    if (t < ntok) src = win_source_token(g, win, t, &grp);
+    sSrc[t] = src;
+    sGrp[t] = static_cast<uint8_t>(grp);
+  }
+  __syncthreads();
+  {
+    const uint32_t sq = smem_u32(sQ), sk = smem_u32(sK), sv = smem_u32(sV);
+    // 8 lanes move one 128-byte row of q, k and v each.
+    for (int idx = tid; idx < npad * 8; idx += kAttnThreads) {
+      const int t = idx >> 3;
+      const int chunk = idx & 7;
+      const int src = sSrc[t];
+      const uint32_t off = swz(t, chunk);
+      if (src >= 0) {
+        const __nv_bfloat16* p = a.qkv + (row_base + src) * ld + head * kHeadDim + chunk * 8;
+        cp_async_16(sq + off, p);
+        cp_async_16(sk + off, p + a.dim);
+        cp_async_16(sv + off, p + 2 * a.dim);
+      } else if (src == -1) {
+        // zero-padded token: x = 0, so q|k|v equal the projection bias (swin3d.py:476-482)
+        const __nv_bfloat16* p = a.pad_qkv + head * kHeadDim + chunk * 8;
+        cp_async_16(sq + off, p);
+        cp_async_16(sk + off, p + a.dim);
+        cp_async_16(sv + off, p + 2 * a.dim);
+      } else {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(sQ + off) = z;
+        *reinterpret_cast<uint4*>(sK + off) = z;
+        *reinterpret_cast<uint4*>(sV + off) = z;
+      }
+    }
+    cp_async_wait_all();
+  }
+  __syncthreads();
+
+  const int r0 = warp * 16;
+  if (r0 < npad) {
+    // ---- 2. attention for query rows [r0, r0+16) -------------------------------------------------
+    const uint32_t sq = smem_u32(sQ), sk = smem_u32(sK), sv = smem_u32(sV);
+    uint32_t qf[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+      ldsm_x4(sq + swz(r0 + (lane & 15), kk * 2 + (lane >> 4)), qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3]);
+
+    const int qrow0 = r0 + (lane >> 2);  // this thread's two query rows: qrow0, qrow0 + 8
+    const int qrow1 = qrow0 + 8;
+    const int gq0 = sGrp[qrow0], gq1 = sGrp[qrow1];
+    constexpr float kLog2e = 1.4426950408889634f;
+    constexpr float kScale = 0.125f * kLog2e;  // 1/sqrt(64), in the exp2 domain
+    constexpr float kMasked = -100.0f * kLog2e;
+
+    float o[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+    for (int kb = 0; kb < npad; kb += kKeyBlock) {
+      float s[6][4];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+      for (int jp = 0; jp < 3; ++jp) {
+        const int n0 = kb + jp * 16;
+        if (n0 < npad) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4(sk + swz(n0 + (lane & 7) + ((lane >> 4) << 3), kk * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
+            mma_bf16_16816(s[2 * jp], qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], b0, b1);
+            mma_bf16_16816(s[2 * jp + 1], qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], b2, b3);
+          }
+        }
+      }
+      // scale, mask, optional bias; running max
+      float mx0 = m0, mx1 = m1;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = kb + j * 8 + (lane & 3) * 2 + (e & 1);
+          const int qrow = (e < 2) ? qrow0 : qrow1;
+          float v = s[j][e] * kScale;
+          if (key >= ntok) {
+            v = -INFINITY;
+          } else {
+            if (a.bias != nullptr && qrow < ntok)
+              v += kLog2e * __ldg(a.bias + (static_cast<size_t>(head) * ntok + qrow) * ntok + key);
+            if (g.shifted) {
+              const int gk = sGrp[key];
+              if (gk != ((e < 2) ? gq0 : gq1)) v += kMasked;
+            }
+          }
+          s[j][e] = v;
+          if (e < 2) mx0 = fmaxf(mx0, v);
+          else mx1 = fmaxf(mx1, v);
+        }
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float alpha0 = exp2f(m0 - mx0), alpha1 = exp2f(m1 - mx1);
+      m0 = mx0;
+      m1 = mx1;
+      float sum0 = 0.f, sum1 = 0.f;
+      uint32_t pf[3][4];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const float p0 = exp2f(s[j][0] - m0), p1 = exp2f(s[j][1] - m0);
+        const float p2 = exp2f(s[j][2] - m1), p3 = exp2f(s[j][3] - m1);
+        sum0 += p0 + p1;
+        sum1 += p2 + p3;
+        pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+        pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+      }
+      l0 = l0 * alpha0 + sum0;
+      l1 = l1 * alpha1 + sum1;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j][0] *= alpha0;
+        o[j][1] *= alpha0;
+        o[j][2] *= alpha1;
+        o[j][3] *= alpha1;
+      }
+      // O += P V
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const int k0 = kb + t * 16;
+        if (k0 < npad) {
+#pragma unroll
+          for (int jp = 0; jp < 4; ++jp) {
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4_trans(sv + swz(k0 + (lane & 7) + (((lane >> 3) & 1) << 3), jp * 2 + (lane >> 4)), b0, b1, b2, b3);
+            mma_bf16_16816(o[2 * jp], pf[t][0], pf[t][1], pf[t][2], pf[t][3], b0, b1);
+            mma_bf16_16816(o[2 * jp + 1], pf[t][0], pf[t][1], pf[t][2], pf[t][3], b2, b3);
+          }
+        }
+      }
+    }
+    // ---- 3. normalise, stage in this warp's own Q rows, coalesced scatter -----------------------
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // columns j*8 + (lane&3)*2 .. +1  -> chunk j, byte offset (lane&3)*4 inside the chunk
+      *reinterpret_cast<uint32_t*>(sQ + swz(qrow0, j) + (lane & 3) * 4) = pack_bf16x2(o[j][0] * inv0, o[j][1] * inv0);
+      *reinterpret_cast<uint32_t*>(sQ + swz(qrow1, j) + (lane & 3) * 4) = pack_bf16x2(o[j][2] * inv1, o[j][3] * inv1);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int row = r0 + it * 4 + (lane >> 3);
+      const int chunk = lane & 7;
+      const int src = sSrc[row];
+      if (src >= 0) {
+        const uint4 v = *reinterpret_cast<const uint4*>(sQ + swz(row, chunk));
+        *reinterpret_cast<uint4*>(a.out + (row_base + src) * a.dim + head * kHeadDim + chunk * 8) = v;
+      }
+    }
+  }
+}
+
+__global__ void window_index_dump_kernel(const WinGeom g, int* idx, uint8_t* grp) {
+  const int total = g.nwindows * g.ntok;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int gr;
+    idx[i] = win_source_token(g, i / g.ntok, i % g.ntok, &gr);
+    grp[i] = static_cast<uint8_t>(gr);
+  }
+}
+
+static size_t attn_smem_bytes(int ntok) {
+  const int npad = (ntok + 15) & ~15;
+  return static_cast<size_t>(npad) * kRowBytes * 3 + npad * sizeof(int) + npad + 16;
+}
+
+}  // namespace ab
+
+extern "C" int ab_window_geometry(const int32_t res[3], const int32_t window[3], const int32_t shift[3],
+                                  int32_t* n_windows, int32_t* n_tokens, int32_t* shifted) {
+  using namespace ab;
+  AB_CHECK_ARG(res && window && shift, "ab_window_geometry: null argument");
+  for (int a = 0; a < 3; ++a)
+    AB_CHECK_ARG(res[a] > 0 && window[a] > 0 && shift[a] >= 0 && shift[a] < window[a],
+                 "ab_window_geometry: bad res/window/shift on axis %d", a);
+  WinGeom g = make_win_geom(res, window, shift, 1);
+  if (n_windows) *n_windows = g.nwindows;
+  if (n_tokens) *n_tokens = g.ntok;
+  if (shifted) *shifted = g.shifted;
+  return AB_OK;
+}
+
+extern "C" int ab_window_index_map(const int32_t res[3], const int32_t window[3], const int32_t shift[3],
+                                   int32_t warped, int32_t* idx_out, uint8_t* group_out, void* stream) {
+  using namespace ab;
+  AB_CHECK_ARG(res && window && shift && idx_out && group_out, "ab_window_index_map: null argument");
+  for (int a = 0; a < 3; ++a)
+    AB_CHECK_ARG(res[a] > 0 && window[a] > 0 && shift[a] >= 0 && shift[a] < window[a],
+                 "ab_window_index_map: bad res/window/shift on axis %d", a);
+  WinGeom g = make_win_geom(res, window, shift, warped);
+  const int total = g.nwindows * g.ntok;
+  window_index_dump_kernel<<<ceil_div(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g, idx_out,
+                                                                                                   group_out);
+  AB_COUNT_LAUNCH(1);
+  AB_CHECK_LAUNCH("ab_window_index_map");
+  return AB_OK;
+}
+
+extern "C" int ab_window_attention(const AbWindowAttention* p, void* stream) {
+  using namespace ab;
+  AB_CHECK_ARG(p != nullptr && p->qkv != nullptr && p->out != nullptr, "ab_window_attention: null argument");
+  AB_CHECK_ARG(p->head_dim == kHeadDim, "ab_window_attention: head_dim must be 64 (got %d)", p->head_dim);
+  AB_CHECK_ARG(p->num_heads > 0 && p->batch > 0, "ab_window_attention: bad batch/heads");
+  for (int a = 0; a < 3; ++a)
+    AB_CHECK_ARG(p->res[a] > 0 && p->window[a] > 0 && p->shift[a] >= 0 && p->shift[a] < p->window[a],
+                 "ab_window_attention: bad res/window/shift on axis %d", a);
+  AttnArgs a;
+  a.g = make_win_geom(p->res, p->window, p->shift, p->warped);
+  AB_CHECK_ARG(a.g.ntok <= kMaxTok, "ab_window_attention: window of %d tokens exceeds the supported %d", a.g.ntok,
+               kMaxTok);
+  const bool has_pad = a.g.nwindows * a.g.ntok != p->res[0] * p->res[1] * p->res[2];
+  AB_CHECK_ARG(!has_pad || p->pad_qkv != nullptr,
+               "ab_window_attention: the window grid is zero-padded; pad_qkv (bf16 projection bias) is required");
+  a.qkv = reinterpret_cast<const __nv_bfloat16*>(p->qkv);
+  a.pad_qkv = reinterpret_cast<const __nv_bfloat16*>(p->pad_qkv);
+  a.out = reinterpret_cast<__nv_bfloat16*>(p->out);
+  a.bias = p->bias;
+  a.batch = p->batch;
+  a.num_heads = p->num_heads;
+  a.dim = p->num_heads * kHeadDim;
+  a.tokens_per_batch = static_cast<long long>(p->res[0]) * p->res[1] * p->res[2];
+  const size_t smem = attn_smem_bytes(a.g.ntok);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(window_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(attn_smem_bytes(kMaxTok)));
+    if (e != cudaSuccess) {
+      set_error("ab_window_attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return AB_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const long long items = static_cast<long long>(p->batch) * a.g.nwindows * p->num_heads;
+  AB_CHECK_ARG(items < (1ll << 31), "ab_window_attention: too many work items");
+  window_attention_kernel<<<static_cast<unsigned>(items), kAttnThreads, smem,
+                            reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  AB_COUNT_LAUNCH(1);
+  AB_CHECK_LAUNCH("ab_window_attention");
+  return AB_OK;
+}

@@ -1,0 +1,697 @@
+"""Forward engine: drives the sm_100a kernels of ``libaurora_b200.so`` through its C ABI.
+
+One ``AuroraEngine`` is bound to one set of parameters on one CUDA device.  PyTorch owns every buffer
+(weights, activations, workspace); all arithmetic on the per-step path happens inside the library:
+
+    Batch fields --ab_patchify--> bf16 token matrix --ab_gemm_bf16 (tcgen05)--> patch embeddings
+      -> Perceiver level aggregation (ab_gemm_bf16 / ab_perceiver_attention / ab_ln_mod_residual)
+      -> 3-D Swin U-Net: per block  QKV GEMM -> ab_window_attention -> proj GEMM -> adaLN+residual
+                                    -> fc1 GEMM(+GELU) -> fc2 GEMM -> adaLN+residual
+         with ab_patch_merge_ln / ab_patch_split_ln between stages
+      -> Perceiver level de-aggregation -> head GEMMs --ab_unpatchify--> output Batch fields
+
+Follows `Aurora.forward` (aurora/model/aurora.py:265-392) and the modules it calls; each method cites
+the reference lines it replaces.  Numerics: bf16 GEMM operands, fp32 accumulation, fp32 residual
+stream / LayerNorm statistics / softmax (the reference's ``autocast=True`` recipe, applied to the
+encoder and decoder as well).
+
+There is NO CPU path: tensors that are not on a CUDA device raise.
+"""
+
+from __future__ import annotations
+
+import dataclasses
+import math
+from datetime import timedelta
+from typing import Optional
+
+import numpy as np
+import torch
+
+from aurora_b200 import cabi, encodings as E
+from aurora_b200.batch import Batch, Metadata
+from aurora_b200.spec import DYNAMIC_VARS, ModelConfig
+from aurora_b200.stats import atmos_stats_of, level_to_str, surf_stats_of
+
+__all__ = ["AuroraEngine"]
+
+GELU = cabi.AB_ACT_GELU_ERF
+
+# AuroraAirPollution._predict_difference_history_dim_lookup (aurora.py:652-666)
+AIR_DIFF_DIM = {"pm1": 0, "pm2p5": 0, "pm10": 0, "co": 1, "tcco": 1, "no": 0, "tc_no": 0, "no2": 0, "tcno2": 0,
+                "so2": 1, "tcso2": 1, "go3": 1, "gtco3": 1}
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def stage_resolutions(patch_res, n_stages):
+    """Per-stage token grids and the odd-size merge paddings (swin3d.py:868-882)."""
+    all_res, padded = [tuple(patch_res)], []
+    for _ in range(1, n_stages):
+        c, h, w = all_res[-1]
+        padded.append((0, h % 2, w % 2))
+        all_res.append((c, (h + h % 2) // 2, (w + w % 2) // 2))
+    padded.append((0, 0, 0))
+    return all_res, padded
+
+
+class AuroraEngine:
+    """Runs `Aurora.forward` for one parameter set on one CUDA device."""
+
+    def __init__(self, cfg: ModelConfig, params: dict[str, torch.Tensor], variant: str = "base") -> None:
+        self.cfg = cfg
+        self.variant = variant
+        some = next(iter(params.values()))
+        if not some.is_cuda:
+            raise RuntimeError(
+                "aurora_b200 runs on CUDA devices only (sm_100a kernels); move the model with .to('cuda'). "
+                "There is no CPU fallback."
+            )
+        self.device = some.device
+        self.p = params  # fp32 master parameters (not copied)
+        if cfg.enc_depth != 1 or cfg.dec_depth != 1:
+            raise NotImplementedError("aurora_b200 supports Perceiver depth 1 (all published presets)")
+        for heads, dim in self._stage_heads_dims():
+            if dim % heads != 0 or dim // heads != 64:
+                raise NotImplementedError("aurora_b200's window attention kernel requires head_dim == 64")
+        if cfg.patch_size <= 0 or cfg.embed_dim % 8 != 0:
+            raise ValueError("bad patch size / embedding dimension")
+        cabi.lib()  # fail loudly now if the CUDA library is missing
+        self._w: dict = {}      # packed bf16 weights / fp32 vectors
+        self._buf: dict = {}    # workspace
+        self._lora: dict = {}   # lora index -> merged qkv/proj weights
+        self._grid_cache: Optional[tuple] = None
+        self._level_cache: dict = {}
+        self._prepare_static()
+
+    # ------------------------------------------------------------------------------------------
+    # parameter packing (once per parameter set; the analogue of a post-load hook, aurora.py:432-456)
+    # ------------------------------------------------------------------------------------------
+    def _stage_heads_dims(self):
+        cfg = self.cfg
+        n_enc, n_dec = len(cfg.encoder_depths), len(cfg.decoder_depths)
+        out = [(cfg.encoder_num_heads[i], cfg.embed_dim * 2**i) for i in range(n_enc)]
+        out += [(cfg.decoder_num_heads[i], cfg.embed_dim * 2 ** (n_dec - i - 1)) for i in range(n_dec)]
+        return out
+
+    def _bf16(self, key: str) -> torch.Tensor:
+        t = self._w.get(("bf16", key))
+        if t is None:
+            t = self.p[key].detach().to(torch.bfloat16).contiguous()
+            self._w[("bf16", key)] = t
+        return t
+
+    def _f32(self, key: str) -> torch.Tensor:
+        return self.p[key].detach().contiguous()
+
+    def _vec(self, name: str, fn) -> torch.Tensor:
+        t = self._w.get(("vec", name))
+        if t is None:
+            t = fn().contiguous()
+            self._w[("vec", name)] = t
+        return t
+
+    def _prepare_static(self) -> None:
+        cfg, dev = self.cfg, self.device
+        d0 = cfg.embed_dim
+        hours = cfg.timestep / timedelta(hours=1)
+        # c = time_mlp(lead_time_expansion(hours))  (swin3d.py:912-914)
+        lead = E.fourier_expansion(torch.tensor([hours], dtype=torch.float32), d0, E.LEAD_RANGE).to(dev)
+        h = cabi.linear_small(lead, self._f32("backbone.time_mlp.0.weight"), self._f32("backbone.time_mlp.0.bias"),
+                              silu_out=True)
+        self.c = cabi.linear_small(h, self._f32("backbone.time_mlp.2.weight"), self._f32("backbone.time_mlp.2.bias"))
+        # encoder lead-time embedding (encoder.py:352-356)
+        lead_h = cfg.timestep.total_seconds() / 3600
+        lead2 = E.fourier_expansion(torch.tensor([lead_h], dtype=torch.float32), d0, E.LEAD_RANGE).to(dev)
+        self.lead_emb = cabi.linear_small(lead2, self._f32("encoder.lead_time_embed.weight"),
+                                          self._f32("encoder.lead_time_embed.bias"))[0]
+        # hoisted Perceiver queries: to_q(latents) is the same for every location (encoder.py:185-186)
+        q = cabi.linear_small(self._f32("encoder.atmos_latents"), self._f32("encoder.level_agg.layers.0.0.to_q.weight"))
+        if cfg.stabilise_level_agg:
+            q = torch.nn.functional.layer_norm(
+                q, (q.shape[-1],), self._f32("encoder.level_agg.layers.0.0.ln_q.weight"),
+                self._f32("encoder.level_agg.layers.0.0.ln_q.bias"))
+        self.enc_q = q.contiguous()
+        self._mods: dict = {}
+
+    def _modulation(self, prefix: str, dim: int) -> tuple[torch.Tensor, torch.Tensor]:
+        """(scale, shift) of an AdaptiveLayerNorm: Linear(SiLU(c)).chunk(2) with shift FIRST (film.py:48-49);
+        depends only on the model time step, so it is computed once."""
+        m = self._mods.get(prefix)
+        if m is None:
+            mod = cabi.linear_small(self.c, self._f32(f"{prefix}.ln_modulation.1.weight"),
+                                    self._f32(f"{prefix}.ln_modulation.1.bias"), silu_in=True)[0]
+            m = (mod[dim:].contiguous(), mod[:dim].contiguous())  # scale_bias = 0 for every preset
+            self._mods[prefix] = m
+        return m
+
+    def _lora_index(self, step: int) -> Optional[int]:
+        """Which LoRA (if any) is active at this roll-out step (lora.py:104-129)."""
+        cfg = self.cfg
+        if not cfg.use_lora or step >= cfg.lora_steps:
+            return None
+        if cfg.lora_mode == "single":
+            return 0
+        if cfg.lora_mode == "from_second":
+            return None if step == 0 else 0
+        if cfg.lora_mode == "all":
+            return step
+        raise ValueError(f"Invalid mode: {cfg.lora_mode}")
+
+    def _attn_weights(self, prefix: str, lora_idx: Optional[int]):
+        """bf16 qkv / proj weights with the rank-8 LoRA update merged in: W + B A (alpha / r = 1)."""
+        key = (prefix, lora_idx)
+        w = self._lora.get(key)
+        if w is None:
+            if self.cfg.lora_mode == "all" and len(self._lora) > 4 * 64:
+                self._lora.clear()  # one merged copy per step would not fit; keep a sliding set
+            wq, wp = self.p[f"{prefix}.attn.qkv.weight"].detach(), self.p[f"{prefix}.attn.proj.weight"].detach()
+            if lora_idx is not None:
+                a = self.p[f"{prefix}.attn.lora_qkv.loras.{lora_idx}.lora_A"].detach()
+                b = self.p[f"{prefix}.attn.lora_qkv.loras.{lora_idx}.lora_B"].detach()
+                wq = wq + b @ a
+                a = self.p[f"{prefix}.attn.lora_proj.loras.{lora_idx}.lora_A"].detach()
+                b = self.p[f"{prefix}.attn.lora_proj.loras.{lora_idx}.lora_B"].detach()
+                wp = wp + b @ a
+            w = (wq.to(torch.bfloat16).contiguous(), wp.to(torch.bfloat16).contiguous())
+            self._lora[key] = w
+        return w
+
+    def _buffer(self, name: str, shape, dtype, zero: bool = False) -> torch.Tensor:
+        key = (name, tuple(shape), dtype)
+        t = self._buf.get(key)
+        if t is None:
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
+            self._buf[key] = t
+        return t
+
+    def _embed_weight(self, prefix: str, names: tuple[str, ...], t: int, kpad: int):
+        """Patch-embedding weight as a GEMM operand [D, K]: cat of the per-variable (D,1,T,P,P) kernels cut
+        to the batch's history length (patchembed.py:100-108), K padded with zeros to `kpad`."""
+        key = ("embed", prefix, names, t, kpad)
+        w = self._w.get(key)
+        if w is None:
+            parts = [self.p[f"{prefix}.weights.{n}"].detach()[:, 0, :t].reshape(self.cfg.embed_dim, -1) for n in names]
+            full = torch.cat(parts, dim=1)
+            wk = torch.zeros(full.shape[0], kpad, dtype=torch.bfloat16, device=self.device)
+            wk[:, : full.shape[1]] = full.to(torch.bfloat16)
+            w = wk
+            self._w[key] = w
+        return w
+
+    # ------------------------------------------------------------------------------------------
+    # cached location-independent encodings
+    # ------------------------------------------------------------------------------------------
+    def _pos_scale_embed(self, lat: torch.Tensor, lon: torch.Tensor) -> torch.Tensor:
+        """pos_embed(pos_enc) + scale_embed(scale_enc), (L, D) f32 (encoder.py:334-346); cached per grid."""
+        c = self._grid_cache
+        if c is not None and c[0].shape == lat.shape and c[1].shape == lon.shape and (
+            (c[0] is lat and c[1] is lon) or (torch.equal(c[0], lat) and torch.equal(c[1], lon))
+        ):
+            return c[2]
+        d0 = self.cfg.embed_dim
+        pos, scale = E.pos_scale_encodings(d0, lat.detach().float().cpu(), lon.detach().float().cpu(), self.cfg.patch_size)
+        pos, scale = pos.to(self.device), scale.to(self.device)
+        emb = cabi.linear_small(pos, self._f32("encoder.pos_embed.weight"), self._f32("encoder.pos_embed.bias"))
+        emb = emb + cabi.linear_small(scale, self._f32("encoder.scale_embed.weight"), self._f32("encoder.scale_embed.bias"))
+        self._grid_cache = (lat, lon, emb.contiguous())
+        return self._grid_cache[2]
+
+    def _level_embeds(self, levels: tuple) -> dict:
+        """Pressure-level embeddings of encoder and decoder and the decoder's hoisted queries
+        (encoder.py:323-325, decoder.py:220-226)."""
+        c = self._level_cache.get(levels)
+        if c is None:
+            cfg = self.cfg
+            lv = torch.tensor(levels)
+            enc = E.fourier_expansion(lv, cfg.embed_dim, E.LEVELS_RANGE).to(self.device)
+            dec = E.fourier_expansion(lv, 2 * cfg.embed_dim, E.LEVELS_RANGE).to(self.device)
+            c = {
+                "enc": cabi.linear_small(enc, self._f32("encoder.atmos_levels_embed.weight"),
+                                         self._f32("encoder.atmos_levels_embed.bias")),
+                "dec": cabi.linear_small(dec, self._f32("decoder.atmos_levels_embed.weight"),
+                                         self._f32("decoder.atmos_levels_embed.bias")),
+            }
+            c["dec_q"] = cabi.linear_small(c["dec"], self._f32("decoder.level_decoder.layers.0.0.to_q.weight"))
+            if cfg.dec_separate_perceiver:
+                c["dec_q_alt"] = cabi.linear_small(
+                    c["dec"], self._f32("decoder.level_decoder_alternate.layers.0.0.to_q.weight"))
+            self._level_cache[levels] = c
+        return c
+
+    # ------------------------------------------------------------------------------------------
+    # encoder  (encoder.py:198-366)
+    # ------------------------------------------------------------------------------------------
+    def _field_in(self, tensor, stride_t, loc, scale, transform=cabi.AB_IN_PLAIN, comb=None, const=None):
+        f = cabi.AbFieldIn()
+        if const is not None:
+            f.ptr, f.const_value = None, float(const)
+            f.loc, f.scale = 0.0, 1.0
+            return f
+        f.ptr, f.stride_t = tensor.data_ptr(), int(stride_t)
+        f.loc, f.scale = float(loc), float(scale)
+        f.transform = transform
+        if comb is not None:
+            f.w0, f.w1, f.wb = comb
+        return f
+
+    def _combiner(self, group: str, name: str):
+        w = self.p[f"{group}.{name}.weight"].detach().float().cpu().reshape(-1)
+        b = self.p[f"{group}.{name}.bias"].detach().float().cpu().reshape(-1)
+        return float(w[0]), float(w[1]), float(b[0])
+
+    def _surf_transform(self, name: str):
+        cfg = self.cfg
+        if name in cfg.positive_surf_vars:
+            if self.variant == "air_pollution":
+                return cabi.AB_IN_CLAMP_LOG_COMBINE, self._combiner("surf_feature_combiner", name)
+            return cabi.AB_IN_CLAMP_MIN0, None
+        return cabi.AB_IN_PLAIN, None
+
+    def _atmos_transform(self, name: str):
+        cfg = self.cfg
+        if name in cfg.positive_atmos_vars:
+            if self.variant == "air_pollution":
+                return cabi.AB_IN_CLAMP_LOG_COMBINE, self._combiner("atmos_feature_combiner", name)
+            return cabi.AB_IN_CLAMP_MIN0, None
+        return cabi.AB_IN_PLAIN, None
+
+    def _dynamic_values(self, tm) -> list[float]:
+        return [
+            float(np.cos(2 * np.pi * tm.hour / 24)), float(np.sin(2 * np.pi * tm.hour / 24)),
+            float(np.cos(2 * np.pi * tm.weekday() / 7)), float(np.sin(2 * np.pi * tm.weekday() / 7)),
+            float(np.cos(2 * np.pi * tm.day / 365.25)), float(np.sin(2 * np.pi * tm.day / 365.25)),
+        ]
+
+    def _encode(self, batch: Batch, b: int, x_f32: torch.Tensor, x_b16: torch.Tensor) -> None:
+        """Fill x (4L, D) for batch element `b`.  `batch` holds physical-unit CUDA fp32 fields, cropped."""
+        cfg = self.cfg
+        d0, p = cfg.embed_dim, cfg.patch_size
+        surf_stats = dict(cfg.surf_stats) if cfg.surf_stats else None
+        levels = tuple(batch.metadata.atmos_levels)
+        some = next(iter(batch.surf_vars.values()))
+        t_hist, h, w = some.shape[1], some.shape[2], some.shape[3]
+        l = (h // p) * (w // p)
+        n_lev = len(levels)
+        tm = batch.metadata.time[b]
+
+        # ---- field tables (the order of the batch's dicts, as encoder.py:208-267) ----
+        surf_names = tuple(batch.surf_vars)
+        static_names = tuple(batch.static_vars)
+        atmos_names = tuple(batch.atmos_vars)
+        fields_s, names_s = [], []
+        for k in surf_names:
+            loc, sc = surf_stats_of(k, surf_stats)
+            tr, comb = self._surf_transform(k)
+            v = batch.surf_vars[k]
+            fields_s.append(self._field_in(v[b], h * w, loc, sc, tr, comb))
+            names_s.append(k)
+        static_fields = []
+        for k in static_names:
+            loc, sc = surf_stats_of(k, surf_stats)
+            static_fields.append(self._field_in(batch.static_vars[k], 0, loc, sc))
+        dyn_fields, dyn_names = [], ()
+        if cfg.dynamic_vars:
+            dyn_fields = [self._field_in(None, 0, 0, 1, const=v) for v in self._dynamic_values(tm)]
+            dyn_names = DYNAMIC_VARS
+        fields_s = fields_s + static_fields + dyn_fields
+        names_s = tuple(names_s) + static_names + dyn_names
+
+        # surface patch embedding + level encoding + Perceiver-like MLP (encoder.py:286-288, 316-320)
+        ks = len(fields_s) * t_hist * p * p
+        ks_pad = _round_up(ks, 64)
+        a_s = self._buffer("enc.A_surf", (l, ks_pad), torch.bfloat16, zero=True)
+        cabi.patchify(fields_s, t_hist, h, w, p, a_s)
+        w_s = self._embed_weight("encoder.surf_token_embeds", names_s, t_hist, ks_pad)
+        b_s = self._vec("enc.surf_bias", lambda: self._f32("encoder.surf_token_embeds.bias")
+                        + self._f32("encoder.surf_level_encoding"))
+        xs0 = self._buffer("enc.xs0", (l, d0), torch.float32)
+        xs0_b = self._buffer("enc.xs0_b", (l, d0), torch.bfloat16)
+        cabi.gemm(a_s, w_s, bias=b_s, out_f32=xs0, out_bf16=xs0_b)
+        hid = int(d0 * cfg.mlp_ratio)
+        hbuf = self._buffer("enc.h", ((cfg.latent_levels - 1) * l, hid), torch.bfloat16)
+        mbuf = self._buffer("enc.m", ((cfg.latent_levels - 1) * l, d0), torch.bfloat16)
+        cabi.gemm(xs0_b, self._bf16("encoder.surf_mlp.net.0.weight"), bias=self._f32("encoder.surf_mlp.net.0.bias"),
+                  out_bf16=hbuf[:l], act=GELU)
+        cabi.gemm(hbuf[:l], self._bf16("encoder.surf_mlp.net.2.weight"), bias=self._f32("encoder.surf_mlp.net.2.bias"),
+                  out_bf16=mbuf[:l])
+        # time embeddings (encoder.py:351-363); absolute time via datetime.timestamp() like the reference
+        abs_h = torch.tensor([tm.timestamp() / 3600], dtype=torch.float32)
+        abs_enc = E.fourier_expansion(abs_h, d0, E.ABS_TIME_RANGE, assert_range=False).to(self.device)
+        abs_emb = cabi.linear_small(abs_enc, self._f32("encoder.absolute_time_embed.weight"),
+                                    self._f32("encoder.absolute_time_embed.bias"))[0]
+        tvec = self.lead_emb + abs_emb
+        posscale = self._pos_scale_embed(batch.metadata.lat, batch.metadata.lon)
+        cabi.ln_mod_residual(mbuf[:l], scale=self._f32("encoder.surf_norm.weight"),
+                             shift=(self._f32("encoder.surf_norm.bias") + tvec).contiguous(), residual=xs0,
+                             add_rows=posscale, out_f32=x_f32[:l], out_bf16=x_b16[:l])
+
+        # ---- atmospheric patch embedding per level (encoder.py:291-326) ----
+        atmos_names_full = atmos_names
+        static_as_atmos = []
+        if static_names and cfg.atmos_static_vars:
+            if cfg.dynamic_vars:
+                atmos_names_full = atmos_names + tuple(f"static_{v}" for v in static_names + DYNAMIC_VARS)
+            else:
+                atmos_names_full = atmos_names + static_names
+            static_as_atmos = static_fields + dyn_fields
+        bug_swap = None
+        if cfg.simulate_indexing_bug and "z" in atmos_names_full:
+            bug_swap = (atmos_names_full.index("static_z"), atmos_names_full.index("z"))
+        ka = len(atmos_names_full) * t_hist * p * p
+        ka_pad = _round_up(ka, 64)
+        a_a = self._buffer("enc.A_atmos", (l, ka_pad), torch.bfloat16, zero=True)
+        xa = self._buffer("enc.xa", (n_lev * l, d0), torch.bfloat16)
+        lev = self._level_embeds(levels)
+        per_level_stats = {k: atmos_stats_of(k, levels) for k in atmos_names}
+        for ci, lvl in enumerate(levels):
+            fl = []
+            for k in atmos_names:
+                locs, scs = per_level_stats[k]
+                tr, comb = self._atmos_transform(k)
+                v = batch.atmos_vars[k]
+                fl.append(self._field_in(v[b, :, ci], n_lev * h * w, locs[ci], scs[ci], tr, comb))
+            fl = fl + static_as_atmos
+            if bug_swap is not None:
+                fl[bug_swap[0]] = fl[bug_swap[1]]  # `static_z` reads the `z` slice (encoder.py:291-303)
+            cabi.patchify(fl, t_hist, h, w, p, a_a)
+            if not cfg.level_condition:
+                pre = "encoder.atmos_token_embeds"
+            else:
+                pre = f"encoder.atmos_token_embeds.layers.{level_to_str(lvl)}"
+            w_a = self._embed_weight(pre, atmos_names_full, t_hist, ka_pad)
+            bias = self._vec(f"enc.atmos_bias.{pre}.{levels}.{ci}", lambda: self._f32(f"{pre}.bias") + lev["enc"][ci])
+            cabi.gemm(a_a, w_a, bias=bias, out_bf16=xa[ci * l:(ci + 1) * l])
+
+        # ---- level aggregation: 3 shared latents attend over the levels, per location (encoder.py:173-196) ----
+        nl = cfg.latent_levels - 1
+        pre = "encoder.level_agg.layers.0"
+        kv = self._buffer("enc.kv", (n_lev * l, 2 * d0), torch.bfloat16)
+        cabi.gemm(xa, self._bf16(f"{pre}.0.to_kv.weight"), out_bf16=kv)
+        if cfg.stabilise_level_agg:
+            kview = kv[:, :d0]
+            cabi.ln_mod_residual(kview, scale=self._f32(f"{pre}.0.ln_k.weight"), shift=self._f32(f"{pre}.0.ln_k.bias"),
+                                 out_bf16=kview)
+        att = self._buffer("enc.att", (nl * l, d0), torch.bfloat16)
+        cabi.perceiver_attention(self.enc_q, kv, att, nloc=l, num_heads=cfg.num_heads, head_dim=d0 // cfg.num_heads)
+        ao = self._buffer("enc.ao", (nl * l, d0), torch.bfloat16)
+        cabi.gemm(att, self._bf16(f"{pre}.0.to_out.weight"), out_bf16=ao)
+        lat1 = self._buffer("enc.lat1", (nl * l, d0), torch.float32)
+        lat1_b = self._buffer("enc.lat1_b", (nl * l, d0), torch.bfloat16)
+        cabi.ln_mod_residual(ao, scale=self._f32(f"{pre}.2.weight"), shift=self._f32(f"{pre}.2.bias"),
+                             residual=self._f32("encoder.atmos_latents"), res_div=l, res_mod=nl,
+                             out_f32=lat1, out_bf16=lat1_b, eps=cfg.perceiver_ln_eps)
+        cabi.gemm(lat1_b, self._bf16(f"{pre}.1.net.0.weight"), bias=self._f32(f"{pre}.1.net.0.bias"), out_bf16=hbuf,
+                  act=GELU)
+        cabi.gemm(hbuf, self._bf16(f"{pre}.1.net.2.weight"), bias=self._f32(f"{pre}.1.net.2.bias"), out_bf16=mbuf)
+        cabi.ln_mod_residual(mbuf, scale=self._f32(f"{pre}.3.weight"),
+                             shift=(self._f32(f"{pre}.3.bias") + tvec).contiguous(), residual=lat1, add_rows=posscale,
+                             out_f32=x_f32[l:], out_bf16=x_b16[l:], eps=cfg.perceiver_ln_eps)
+
+    # ------------------------------------------------------------------------------------------
+    # backbone  (swin3d.py:884-936)
+    # ------------------------------------------------------------------------------------------
+    def _block(self, prefix: str, x_f32, x_b16, res, heads: int, shifted: bool, lora_idx, out_b16=None) -> None:
+        """One Swin3DTransformerBlock in place on the fp32 stream (swin3d.py:440-509).  `out_b16`, if
+        given, receives the bf16 copy of the block output instead of x_b16 (used to write into a wider
+        buffer, e.g. the skip concatenation)."""
+        l, d = x_f32.shape
+        ws = tuple(self.cfg.window_size)
+        ss = tuple(s // 2 for s in ws) if shifted else (0, 0, 0)
+        wqkv, wproj = self._attn_weights(prefix, lora_idx)
+        qkv = self._buffer("bb.qkv", (l, 3 * d), torch.bfloat16)
+        att = self._buffer("bb.att", (l, d), torch.bfloat16)
+        y = self._buffer("bb.y", (l, d), torch.bfloat16)
+        hid = self._buffer("bb.h", (l, self._f32(f"{prefix}.mlp.fc1.bias").numel()), torch.bfloat16)
+        cabi.gemm(x_b16, wqkv, bias=self._f32(f"{prefix}.attn.qkv.bias"), out_bf16=qkv)
+        pad = self._vec(f"{prefix}.pad_qkv", lambda: self._f32(f"{prefix}.attn.qkv.bias").to(torch.bfloat16))
+        cabi.window_attention(qkv, att, batch=1, res=res, window=ws, shift=ss, num_heads=heads, pad_qkv=pad)
+        cabi.gemm(att, wproj, bias=self._f32(f"{prefix}.attn.proj.bias"), out_bf16=y)
+        sc1, sh1 = self._modulation(f"{prefix}.norm1", d)
+        cabi.ln_mod_residual(y, scale=sc1, shift=sh1, residual=x_f32, out_f32=x_f32, out_bf16=x_b16)
+        cabi.gemm(x_b16, self._bf16(f"{prefix}.mlp.fc1.weight"), bias=self._f32(f"{prefix}.mlp.fc1.bias"),
+                  out_bf16=hid, act=GELU)
+        cabi.gemm(hid, self._bf16(f"{prefix}.mlp.fc2.weight"), bias=self._f32(f"{prefix}.mlp.fc2.bias"), out_bf16=y)
+        sc2, sh2 = self._modulation(f"{prefix}.norm2", d)
+        cabi.ln_mod_residual(y, scale=sc2, shift=sh2, residual=x_f32, out_f32=x_f32,
+                             out_bf16=x_b16 if out_b16 is None else out_b16)
+
+    def _backbone(self, x_f32: torch.Tensor, x_b16: torch.Tensor, patch_res, rollout_step: int) -> torch.Tensor:
+        """U-Net over the token stream; returns the bf16 (L, 2*D0) concatenation [x | skip0]."""
+        cfg = self.cfg
+        d0 = cfg.embed_dim
+        n_enc, n_dec = len(cfg.encoder_depths), len(cfg.decoder_depths)
+        if patch_res[0] % cfg.window_size[0] != 0:
+            raise AssertionError(
+                f"Patch height ({patch_res[0]}) must be divisible by ws[0] ({cfg.window_size[0]})")
+        all_res, padded = stage_resolutions(patch_res, n_enc)
+        lora_idx = self._lora_index(rollout_step)
+        l0 = x_f32.shape[0]
+        concat = self._buffer("bb.concat", (l0, 2 * d0), torch.bfloat16)
+        skips: list[Optional[torch.Tensor]] = []
+        cur_f, cur_b = x_f32, x_b16
+        for i in range(n_enc):
+            res = all_res[i]
+            depth = cfg.encoder_depths[i]
+            dim = d0 * 2**i
+            for j in range(depth):
+                # the bf16 copy of skips[0] goes straight into the right half of the final concatenation
+                # (swin3d.py:933-935); nothing else reads it because the merge consumes the fp32 stream
+                last0 = i == 0 and j == depth - 1 and n_enc > 1
+                self._block(f"backbone.encoder_layers.{i}.blocks.{j}", cur_f, cur_b, res, cfg.encoder_num_heads[i],
+                            j % 2 == 1, lora_idx, out_b16=concat[:, d0:] if last0 else None)
+            if i == 0 and (depth == 0 or n_enc == 1):
+                concat[:, d0:].copy_(cur_b)
+            skips.append(cur_f)
+            if i < n_enc - 1:
+                c, h, w = res
+                pre = f"backbone.encoder_layers.{i}.downsample"
+                nr = all_res[i + 1]
+                rows = nr[0] * nr[1] * nr[2]
+                merged = self._buffer(f"bb.merged{i}", (rows, 4 * dim), torch.bfloat16)
+                cabi.patch_merge_ln(cur_f, self._f32(f"{pre}.norm.weight"), self._f32(f"{pre}.norm.bias"), merged,
+                                    batch=1, c=c, h=h, w=w, d=dim)
+                nxt_f = self._buffer(f"bb.x{i + 1}", (rows, 2 * dim), torch.float32)
+                nxt_b = self._buffer(f"bb.xb{i + 1}", (rows, 2 * dim), torch.bfloat16)
+                cabi.gemm(merged, self._bf16(f"{pre}.reduction.weight"), out_f32=nxt_f, out_bf16=nxt_b)
+                cur_f, cur_b = nxt_f, nxt_b
+        for i in range(n_dec):
+            index = n_dec - i - 1
+            res = all_res[index]
+            dim = d0 * 2**index
+            depth = cfg.decoder_depths[i]
+            final = i == n_dec - 1
+            for j in range(depth):
+                self._block(f"backbone.decoder_layers.{i}.blocks.{j}", cur_f, cur_b, res, cfg.decoder_num_heads[i],
+                            j % 2 == 1, lora_idx,
+                            out_b16=concat[:, :d0] if (final and j == depth - 1) else None)
+            if final and depth == 0:
+                concat[:, :d0].copy_(cur_b)
+            if not final:
+                c, h, w = res
+                crop = padded[index - 1]
+                pre = f"backbone.decoder_layers.{i}.upsample"
+                y2 = self._buffer(f"bb.up_y{i}", (c * h * w, 2 * dim), torch.bfloat16)
+                cabi.gemm(cur_b, self._bf16(f"{pre}.lin1.weight"), out_bf16=y2)
+                nr = all_res[index - 1]
+                rows = nr[0] * nr[1] * nr[2]
+                assert nr[1] == 2 * h - crop[1] and nr[2] == 2 * w - crop[2]
+                sp = self._buffer(f"bb.up_s{i}", (rows, dim // 2), torch.bfloat16)
+                cabi.patch_split_ln(y2, self._f32(f"{pre}.norm.weight"), self._f32(f"{pre}.norm.bias"), sp, batch=1,
+                                    c=c, h=h, w=w, d=dim, crop_h=crop[1], crop_w=crop[2])
+                nxt_f = self._buffer(f"bb.dx{index - 1}", (rows, dim // 2), torch.float32)
+                nxt_b = self._buffer(f"bb.dxb{index - 1}", (rows, dim // 2), torch.bfloat16)
+                # additive skip on the up-sampled output of the intermediate layers (swin3d.py:930-932),
+                # fused into lin2's epilogue
+                skip = skips[index - 1] if 0 < i < n_dec - 1 else None
+                cabi.gemm(sp, self._bf16(f"{pre}.lin2.weight"), residual=skip, out_f32=nxt_f, out_bf16=nxt_b)
+                cur_f, cur_b = nxt_f, nxt_b
+        return concat
+
+    # ------------------------------------------------------------------------------------------
+    # decoder  (decoder.py:168-276)
+    # ------------------------------------------------------------------------------------------
+    def _perceiver_dec(self, name: str, q: torch.Tensor, lev_emb: torch.Tensor, ctx: torch.Tensor, l: int, tag: str):
+        """Level de-aggregation: queries = level embeddings (shared by all locations), context = the 3
+        atmospheric latents of each location (decoder.py:140-166, perceiver.py:212-233)."""
+        cfg = self.cfg
+        e = 2 * cfg.embed_dim
+        n_lev = q.shape[0]
+        pre = f"decoder.{name}.layers.0"
+        kv = self._buffer("dec.kv", (ctx.shape[0], 2 * e), torch.bfloat16)
+        cabi.gemm(ctx, self._bf16(f"{pre}.0.to_kv.weight"), out_bf16=kv)
+        att = self._buffer("dec.att", (n_lev * l, e), torch.bfloat16)
+        cabi.perceiver_attention(q, kv, att, nloc=l, num_heads=cfg.num_heads, head_dim=e // cfg.num_heads)
+        ao = self._buffer("dec.ao", (n_lev * l, e), torch.bfloat16)
+        cabi.gemm(att, self._bf16(f"{pre}.0.to_out.weight"), out_bf16=ao)
+        lat1 = self._buffer("dec.lat1", (n_lev * l, e), torch.float32)
+        lat1_b = self._buffer("dec.lat1_b", (n_lev * l, e), torch.bfloat16)
+        cabi.ln_mod_residual(ao, scale=self._f32(f"{pre}.2.weight"), shift=self._f32(f"{pre}.2.bias"), residual=lev_emb,
+                             res_div=l, res_mod=n_lev, out_f32=lat1, out_bf16=lat1_b, eps=cfg.perceiver_ln_eps)
+        hid = int(e * cfg.dec_mlp_ratio)
+        hbuf = self._buffer("dec.h", (n_lev * l, hid), torch.bfloat16)
+        cabi.gemm(lat1_b, self._bf16(f"{pre}.1.net.0.weight"), bias=self._f32(f"{pre}.1.net.0.bias"), out_bf16=hbuf,
+                  act=GELU)
+        cabi.gemm(hbuf, self._bf16(f"{pre}.1.net.2.weight"), bias=self._f32(f"{pre}.1.net.2.bias"), out_bf16=ao)
+        out = self._buffer(f"dec.lat2.{tag}", (n_lev * l, e), torch.bfloat16)
+        cabi.ln_mod_residual(ao, scale=self._f32(f"{pre}.3.weight"), shift=self._f32(f"{pre}.3.bias"), residual=lat1,
+                             out_bf16=out, eps=cfg.perceiver_ln_eps)
+        return out
+
+    def _head_weight(self, kind: str, names: tuple[str, ...], level=None):
+        """All per-variable heads of one kind concatenated to one GEMM: rows v*P*P + (p1*P + p2)."""
+        key = ("head", kind, names, level)
+        w = self._w.get(key)
+        if w is None:
+            if level is None:
+                ws = [self.p[f"decoder.{kind}.{n}.weight"].detach() for n in names]
+                bs = [self.p[f"decoder.{kind}.{n}.bias"].detach() for n in names]
+            else:
+                ws = [self.p[f"decoder.{kind}.{n}.layers.{level}.weight"].detach() for n in names]
+                bs = [self.p[f"decoder.{kind}.{n}.layers.{level}.bias"].detach() for n in names]
+            w = (torch.cat(ws, 0).to(torch.bfloat16).contiguous(), torch.cat(bs, 0).float().contiguous())
+            self._w[key] = w
+        return w
+
+    def _decode(self, xdec: torch.Tensor, batch: Batch, b: int, patch_res, out_surf: dict, out_atmos: dict,
+                pred_step: int) -> None:
+        cfg = self.cfg
+        p = cfg.patch_size
+        pp = p * p
+        surf_stats = dict(cfg.surf_stats) if cfg.surf_stats else None
+        levels = tuple(batch.metadata.atmos_levels)
+        n_lev = len(levels)
+        c0, hp, wp = patch_res
+        l = hp * wp
+        h, w = hp * p, wp * p
+        air = self.variant == "air_pollution"
+        clamp_now = pred_step >= 1 if cfg.clamp_at_first_step else pred_step > 1
+
+        # ---- surface heads on latent level 0 (decoder.py:214-217) ----
+        surf_in = tuple(batch.surf_vars)
+        surf_names = surf_in + tuple(f"{n}_mod" for n in surf_in if n in cfg.modulation_heads)
+        w_s, b_s = self._head_weight("surf_heads", surf_names)
+        ys = self._buffer("dec.ys", (l, len(surf_names) * pp), torch.float32)
+        cabi.gemm(xdec[:l], w_s, bias=b_s, out_f32=ys)
+        fo = []
+        for k in (surf_in if air else surf_names):
+            loc, sc = surf_stats_of(k, surf_stats)
+            f = cabi.AbFieldOut()
+            f.ptr = out_surf[k][b, 0].data_ptr()
+            f.loc, f.scale = loc, sc
+            f.col = surf_names.index(k) * pp
+            f.mod_col = -1
+            if air and k in AIR_DIFF_DIM:
+                f.mod_col = surf_names.index(f"{k}_mod") * pp
+                f.prev = batch.surf_vars[k][b, AIR_DIFF_DIM[k]].data_ptr()
+            f.clamp_min0 = int(clamp_now and k in cfg.positive_surf_vars)
+            fo.append(f)
+        cabi.unpatchify(fo, ys, h, w, p)
+
+        # ---- level de-aggregation + atmospheric heads (decoder.py:219-263) ----
+        lev = self._level_embeds(levels)
+        ctx = xdec[l:]
+        atmos_in = tuple(batch.atmos_vars)
+        atmos_names = atmos_in + tuple(f"{n}_mod" for n in atmos_in if n in cfg.modulation_heads)
+        sep = cfg.dec_separate_perceiver
+        groups = [("level_decoder", "dec_q", tuple(n for n in atmos_names if n not in sep), "main")]
+        if sep:
+            groups.append(("level_decoder_alternate", "dec_q_alt", tuple(n for n in atmos_names if n in sep), "alt"))
+        ya = self._buffer("dec.ya", (n_lev * l, len(atmos_names) * pp), torch.float32)
+        col_of = {}
+        col = 0
+        for mod_name, qkey, names, tag in groups:
+            if not names:
+                continue
+            xa = self._perceiver_dec(mod_name, lev[qkey], lev["dec"], ctx, l, tag)
+            ncol = len(names) * pp
+            yv = ya[:, col:col + ncol]
+            if not cfg.level_condition:
+                w_a, b_a = self._head_weight("atmos_heads", names)
+                cabi.gemm(xa, w_a, bias=b_a, out_f32=yv)
+            else:
+                for ci, lvl in enumerate(levels):
+                    w_a, b_a = self._head_weight("atmos_heads", names, level_to_str(lvl))
+                    cabi.gemm(xa[ci * l:(ci + 1) * l], w_a, bias=b_a, out_f32=yv[ci * l:(ci + 1) * l])
+            for i, n in enumerate(names):
+                col_of[n] = col + i * pp
+            col += ncol
+        per_level = {k: atmos_stats_of(k, levels) for k in atmos_in} if air else {
+            k: atmos_stats_of(k, levels) for k in atmos_names}
+        for ci, lvl in enumerate(levels):
+            fo = []
+            for k in (atmos_in if air else atmos_names):
+                locs, scs = per_level[k]
+                f = cabi.AbFieldOut()
+                f.ptr = out_atmos[k][b, 0, ci].data_ptr()
+                f.loc, f.scale = locs[ci], scs[ci]
+                f.col = col_of[k]
+                f.mod_col = -1
+                if air and k in AIR_DIFF_DIM:
+                    f.mod_col = col_of[f"{k}_mod"]
+                    f.prev = batch.atmos_vars[k][b, AIR_DIFF_DIM[k], ci].data_ptr()
+                f.clamp_min0 = int(clamp_now and k in cfg.positive_atmos_vars)
+                f.clamp_max1 = int(air and cfg.use_lora and k == "so2" and lvl >= 850)
+                fo.append(f)
+            cabi.unpatchify(fo, ya[ci * l:(ci + 1) * l], h, w, p)
+
+    # ------------------------------------------------------------------------------------------
+    # whole forward  (aurora.py:265-392)
+    # ------------------------------------------------------------------------------------------
+    @torch.inference_mode()
+    def forward(self, batch: Batch) -> Batch:
+        cfg = self.cfg
+        batch = batch.type(torch.float32)
+        batch = batch.crop(patch_size=cfg.patch_size)
+        batch = batch.to(self.device)
+        batch = dataclasses.replace(
+            batch,
+            surf_vars={k: v.contiguous() for k, v in batch.surf_vars.items()},
+            static_vars={k: v.contiguous() for k, v in batch.static_vars.items()},
+            atmos_vars={k: v.contiguous() for k, v in batch.atmos_vars.items()},
+        )
+        h, w = batch.spatial_shape
+        p = cfg.patch_size
+        if h % p != 0 or w % p != 0:
+            raise ValueError("Height and width of the data must be multiples of the patch size.")
+        some = next(iter(batch.surf_vars.values()))
+        bsz, t_hist = some.shape[:2]
+        if t_hist > cfg.max_history_size:
+            raise AssertionError(f"{t_hist} > {cfg.max_history_size}.")
+        patch_res = (cfg.latent_levels, h // p, w // p)
+        l = patch_res[1] * patch_res[2]
+        l_tot = cfg.latent_levels * l
+        d0 = cfg.embed_dim
+        levels = tuple(batch.metadata.atmos_levels)
+        step = batch.metadata.rollout_step
+        air = self.variant == "air_pollution"
+
+        surf_out_names = tuple(batch.surf_vars) if air else tuple(batch.surf_vars) + tuple(
+            f"{n}_mod" for n in batch.surf_vars if n in cfg.modulation_heads)
+        atmos_out_names = tuple(batch.atmos_vars) if air else tuple(batch.atmos_vars) + tuple(
+            f"{n}_mod" for n in batch.atmos_vars if n in cfg.modulation_heads)
+        out_surf = {k: torch.empty(bsz, 1, h, w, dtype=torch.float32, device=self.device) for k in surf_out_names}
+        out_atmos = {k: torch.empty(bsz, 1, len(levels), h, w, dtype=torch.float32, device=self.device)
+                     for k in atmos_out_names}
+
+        x_f32 = self._buffer("x0", (l_tot, d0), torch.float32)
+        x_b16 = self._buffer("xb0", (l_tot, d0), torch.bfloat16)
+        for b in range(bsz):
+            self._encode(batch, b, x_f32, x_b16)
+            xdec = self._backbone(x_f32, x_b16, patch_res, step)
+            self._decode(xdec, batch, b, patch_res, out_surf, out_atmos, step + 1)
+
+        return Batch(
+            surf_vars=out_surf,
+            static_vars=dict(batch.static_vars),
+            atmos_vars=out_atmos,
+            metadata=Metadata(
+                lat=batch.metadata.lat,
+                lon=batch.metadata.lon,
+                time=tuple(tm + cfg.timestep for tm in batch.metadata.time),
+                atmos_levels=batch.metadata.atmos_levels,
+                rollout_step=step + 1,
+            ),
+        )

@@ -74,6 +74,147 @@ typedef struct AbGemm {
 
 int ab_gemm_bf16(const AbGemm* g, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * 3-D shifted-window attention — replaces, for one Swin3DTransformerBlock (swin3d.py:440-509):
+ *   torch.roll (:472,:501), pad_3d / crop_3d (:482,:497), window_partition_3d / window_reverse_3d
+ *   (:485,:494), compute_3d_shifted_window_mask (:303-360), maybe_adjust_windows (util.py:53-71) and
+ *   F.scaled_dot_product_attention (:164,:166).
+ *
+ * qkv : bf16 [batch*C*H*W, 3*D], the QKV projection of the FLAT token stream (row = (c*H + h)*W + w,
+ *       columns [q | k | v], each head-major with head_dim 64: the layout nn.Linear(D, 3D) produces).
+ * out : bf16 [batch*C*H*W, D], heads merged, written at the source token of every window position.
+ * `window`/`shift` are the CONFIGURED sizes (e.g. {2,6,12} / {1,3,6} or {0,0,0}); clamping to the
+ * resolution, two-sided zero padding, the cyclic shift and the 0/-100 group mask (only when shifted;
+ * `warped` merges the left/right longitude groups) are computed in-kernel.  Zero-padded positions
+ * take q|k|v from pad_qkv (bf16 [3*D] = the projection bias, because x = 0 there) and are attended to
+ * exactly as the reference does in unshifted blocks.  `bias` is an optional dense additive term
+ * f32 [num_heads, N, N] (N = tokens per window); NULL for every shipped Aurora checkpoint.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct AbWindowAttention {
+  const void* qkv;
+  const void* pad_qkv; /* bf16 [3*D]; required when the window grid is zero-padded */
+  void* out;
+  const float* bias;   /* optional, usually NULL */
+  int32_t batch;
+  int32_t res[3];      /* C, H, W */
+  int32_t window[3];
+  int32_t shift[3];
+  int32_t num_heads;
+  int32_t head_dim;    /* must be 64 */
+  int32_t warped;
+} AbWindowAttention;
+
+int ab_window_attention(const AbWindowAttention* p, void* stream);
+
+/* Window bookkeeping of one block: number of windows per batch element, tokens per (clamped) window
+ * and whether the group mask applies.  Host-only, no launch. */
+int ab_window_geometry(const int32_t res[3], const int32_t window[3], const int32_t shift[3],
+                       int32_t* n_windows, int32_t* n_tokens, int32_t* shifted);
+
+/* Test hook: materialise the in-kernel index arithmetic.  idx_out int32 [n_windows*n_tokens] receives
+ * the source token of every window position (-1 = zero padding), group_out uint8 the mask group id
+ * (27 = padding).  Must equal roll -> pad -> window_partition_3d / compute_3d_shifted_window_mask. */
+int ab_window_index_map(const int32_t res[3], const int32_t window[3], const int32_t shift[3], int32_t warped,
+                        int32_t* idx_out, uint8_t* group_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm + modulation + residual, one pass over the token stream:
+ *
+ *   out[r, :] = residual[rr, :] + LN(y[r, :]) * scale + shift + add_rows[r % add_mod, :]
+ *
+ * Replaces AdaptiveLayerNorm + the residual adds of a Swin block (film.py:48-49, swin3d.py:507-508:
+ * scale = scale_bias + scale(c), shift = shift(c), both precomputed vectors), the post-res-norm of the
+ * Perceiver blocks (perceiver.py:225-232: scale/shift = LayerNorm affine, residual = latents broadcast
+ * with rr = (r / res_div) % res_mod) and the encoder's surface MLP residual plus position / scale /
+ * time embeddings (encoder.py:320, 344-363: add_rows).  LN statistics in fp32, eps as given.
+ * y: bf16 [rows, ld_y]; scale/shift: f32 [dim] or NULL (1 / 0); residual: f32 or NULL; res_mod == 0 means
+ * rr = r.  Outputs: f32 and/or bf16, may alias `residual` (each row is read before it is written) and
+ * out_bf16 may alias `y`.  dim % 8 == 0, dim <= 4096.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct AbLnModResidual {
+  const void* y;
+  const float* scale;
+  const float* shift;
+  const float* residual;
+  const float* add_rows;
+  float* out_f32;
+  void* out_bf16;
+  int64_t rows;
+  int64_t res_div, res_mod;
+  int64_t add_mod;
+  int32_t dim;
+  int32_t ld_y, ld_res, ld_f32, ld_bf16;
+  float eps;
+} AbLnModResidual;
+
+int ab_ln_mod_residual(const AbLnModResidual* p, void* stream);
+
+/* PatchMerging3D front half (swin3d.py:526-553): x f32 [batch, C, H, W, D] -> zero pad H, W to even at
+ * the bottom / right -> 2x2 gather with feature order (h w D) -> LayerNorm(4D) with affine gamma/beta
+ * -> bf16 [batch*C*ceil(H/2)*ceil(W/2), 4D], the A operand of `reduction` (ab_gemm_bf16). */
+int ab_patch_merge_ln(const float* x, const float* gamma, const float* beta, void* out_bf16, int32_t batch,
+                      int32_t c, int32_t h, int32_t w, int32_t d, float eps, void* stream);
+
+/* PatchSplitting3D middle (swin3d.py:585-611): y bf16 [batch*C*H*W, 2D] (output of lin1) -> view
+ * (.., 2, 2, D/2) pixel shuffle to (2H, 2W) -> crop the merge padding (crop_h, crop_w in {0,1}, removed at
+ * the bottom / right) -> LayerNorm(D/2) affine -> bf16 [batch*C*(2H-crop_h)*(2W-crop_w), D/2], the A
+ * operand of lin2.  `d` is the layer's input dimension D. */
+int ab_patch_split_ln(const void* y_bf16, const float* gamma, const float* beta, void* out_bf16, int32_t batch,
+                      int32_t c, int32_t h, int32_t w, int32_t d, int32_t crop_h, int32_t crop_w, float eps,
+                      void* stream);
+
+/* Perceiver cross-attention core (perceiver.py:148-151) for location-independent queries:
+ * q f32 [lq, D] (= to_q(latents), computed once), kv bf16 [lk*nloc, ld_kv] with row = ck*nloc + loc and
+ * columns [k | v]; out bf16 [lq*nloc, ld_out], row = cq*nloc + loc.  softmax(q k^T / sqrt(head_dim)) v
+ * per (location, head); head_dim 32 or 64. */
+int ab_perceiver_attention(const float* q, const void* kv_bf16, void* out_bf16, int64_t nloc, int32_t lq,
+                           int32_t lk, int32_t num_heads, int32_t head_dim, int32_t ld_kv, int32_t ld_out,
+                           void* stream);
+
+/* y f32 [rows, n] = silu_out?( silu_in?(x f32 [rows, k]) W^T + bias ), W f32 [n, k]: the handful of
+ * location-independent vectors (time MLP swin3d.py:805-809,914; adaLN modulation film.py:27-28; level,
+ * lead-time and absolute-time embeddings encoder.py:323-325,352-363, decoder.py:220-223). */
+int ab_linear_small_f32(const float* x, const float* w, const float* bias, float* y, int32_t rows, int32_t n,
+                        int32_t k, int32_t silu_in, int32_t silu_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batch <-> token matrix.  Field descriptors are HOST arrays (copied into the launch).
+ * ---------------------------------------------------------------------------------------------- */
+#define AB_MAX_FIELDS 40
+
+enum { AB_IN_PLAIN = 0, AB_IN_CLAMP_MIN0 = 1, AB_IN_CLAMP_LOG_COMBINE = 2 };
+
+typedef struct AbFieldIn {
+  const float* ptr;   /* (T, H, W) planes of one variable (one batch element, one level); NULL = constant */
+  int64_t stride_t;   /* elements between history steps (0 for static variables) */
+  float loc, scale;   /* normalisation (x - loc) / scale   (batch.py:94-116, normalisation.py:34-70) */
+  float const_value;  /* normalised value when ptr == NULL (dynamic time-of-day style variables) */
+  int32_t transform;  /* AB_IN_* : positive clamp (aurora.py:302-317) / AirPollution combiner (:733-742) */
+  float w0, w1, wb;   /* combiner Linear(2,1) weights and bias */
+} AbFieldIn;
+
+/* out bf16 [ (H/p)*(W/p), ldk ] with column ((v*t_hist + t)*p + p1)*p + p2 = transform(field v at history t,
+ * pixel (hp*p + p1, wp*p + p2)); columns >= nfields*t_hist*p*p are left untouched (keep them zero).
+ * Replaces Batch.normalise + torch.stack (encoder.py:213-215) + conv3d im2col (patchembed.py:100-112). */
+int ab_patchify(const AbFieldIn* fields, int32_t nfields, int32_t t_hist, int32_t h, int32_t w, int32_t p,
+                void* out_bf16, int32_t ldk, void* stream);
+
+typedef struct AbFieldOut {
+  float* ptr;         /* (H, W) output plane, physical units */
+  const float* prev;  /* previous state plane (row pitch W), physical units; needed when mod_col >= 0 */
+  float loc, scale;   /* un-normalisation y * scale + loc (batch.py:118-140) */
+  int32_t col;        /* first of the p*p head columns of this variable in y */
+  int32_t mod_col;    /* first column of its modulation head (aurora.py:767-775) or -1 */
+  int32_t clamp_min0; /* positive-variable clamp (aurora.py:367-388) */
+  int32_t clamp_max1; /* AirPollution SO2 >= 850 hPa clamp (aurora.py:787-794) */
+} AbFieldOut;
+
+/* y f32 [ (H/p)*(W/p), ldy ] (head GEMM output, column col + p1*p + p2) -> planes.  Replaces torch.stack +
+ * unpatchify (decoder.py:214-217,250-263; util.py:18-41), the post-decoder hooks and Batch.unnormalise. */
+int ab_unpatchify(const AbFieldOut* fields, int32_t nfields, const float* y, int32_t ldy, int32_t h, int32_t w,
+                  int32_t p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
