@@ -45,7 +45,20 @@ class AbGemm(C.Structure):
         ("ld_f32", C.c_int32),
         ("ld_bf16", C.c_int32),
         ("act", C.c_int32),
+        ("in_dtype", C.c_int32),
+        ("out_dtype", C.c_int32),
     ]
+
+
+AB_DT_BF16, AB_DT_F16 = 0, 1
+_DT = {torch.bfloat16: AB_DT_BF16, torch.float16: AB_DT_F16}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise AbError(f"expected a bf16 or fp16 tensor, got {t.dtype}") from None
 
 
 _lib: Optional[C.CDLL] = None
@@ -79,6 +92,7 @@ EXPORTS = [
     "ab_window_attention",
     "ab_window_geometry",
     "ab_window_index_map",
+    "ab_window_index_map_host",
     "ab_ln_mod_residual",
     "ab_patch_merge_ln",
     "ab_patch_split_ln",
@@ -89,6 +103,29 @@ EXPORTS = [
 ]
 AB_MAX_FIELDS = 40
 AB_IN_PLAIN, AB_IN_CLAMP_MIN0, AB_IN_CLAMP_LOG_COMBINE = 0, 1, 2
+
+
+# Optional per-call device timing (bench.py's roofline leg): when PROFILE is a dict, every op wrapper
+# records a CUDA-event pair on the current stream under its kernel name.
+PROFILE: Optional[dict] = None
+
+
+class _Timed:
+    def __init__(self, name: str, work: float = 0.0, nbytes: float = 0.0):
+        self.name, self.work, self.nbytes = name, work, nbytes
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.setdefault(self.name, []).append((self.e0, self.e1, self.work, self.nbytes))
+        return False
 
 
 def check(status: int, what: str = "") -> None:
@@ -130,7 +167,7 @@ def gemm(
     act: int = AB_ACT_NONE,
 ) -> None:
     """``out = act(a @ w.T + bias) + residual`` on the tcgen05 GEMM (a, w bf16; outputs preallocated)."""
-    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    assert a.dtype == w.dtype, (a.dtype, w.dtype)
     m, k = a.shape
     n, k2 = w.shape
     assert k == k2, f"K mismatch {k} vs {k2}"
@@ -150,11 +187,14 @@ def gemm(
     if out_f32 is not None:
         assert out_f32.dtype == torch.float32 and out_f32.shape == (m, n)
         g.ld_f32 = _ld(out_f32)
+    g.in_dtype = _dt(a)
     if out_bf16 is not None:
-        assert out_bf16.dtype == torch.bfloat16 and out_bf16.shape == (m, n)
+        assert out_bf16.shape == (m, n)
         g.ld_bf16 = _ld(out_bf16)
+        g.out_dtype = _dt(out_bf16)
     g.act = act
-    check(lib().ab_gemm_bf16(C.byref(g), C.c_void_p(stream_ptr())), "ab_gemm_bf16")
+    with _Timed("gemm", work=2.0 * m * n * k):
+        check(lib().ab_gemm_bf16(C.byref(g), C.c_void_p(stream_ptr())), "ab_gemm_bf16")
 
 
 class AbWindowAttention(C.Structure):
@@ -192,6 +232,8 @@ class AbLnModResidual(C.Structure):
         ("ld_f32", C.c_int32),
         ("ld_bf16", C.c_int32),
         ("eps", C.c_float),
+        ("in_dtype", C.c_int32),
+        ("out_dtype", C.c_int32),
     ]
 
 
@@ -248,6 +290,19 @@ def window_index_map(res, window, shift, warped: bool = True, device="cuda"):
     return idx.view(nw, nt), grp.view(nw, nt)
 
 
+def window_index_map_host(res, window, shift, warped: bool = True):
+    """The same index arithmetic evaluated on the host (numpy arrays); needs no GPU."""
+    import numpy as np
+
+    nw, nt, _ = window_geometry(res, window, shift)
+    idx = np.empty(nw * nt, dtype=np.int32)
+    grp = np.empty(nw * nt, dtype=np.uint8)
+    check(lib().ab_window_index_map_host(_i3(res), _i3(window), _i3(shift), C.c_int32(int(warped)),
+                                         idx.ctypes.data_as(C.c_void_p), grp.ctypes.data_as(C.c_void_p)),
+          "ab_window_index_map_host")
+    return idx.reshape(nw, nt), grp.reshape(nw, nt)
+
+
 def window_attention(qkv: torch.Tensor, out: torch.Tensor, *, batch: int, res, window, shift, num_heads: int,
                      pad_qkv: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
                      warped: bool = True) -> None:
@@ -266,15 +321,18 @@ def window_attention(qkv: torch.Tensor, out: torch.Tensor, *, batch: int, res, w
     a.batch = batch
     a.res, a.window, a.shift = _i3(res), _i3(window), _i3(shift)
     a.num_heads, a.head_dim, a.warped = num_heads, 64, int(warped)
-    check(lib().ab_window_attention(C.byref(a), _s()), "ab_window_attention")
+    nw, nt, _ = window_geometry(res, window, shift)
+    with _Timed("window_attention", work=4.0 * batch * nw * num_heads * nt * nt * 64, nbytes=8.0 * tokens * d):
+        check(lib().ab_window_attention(C.byref(a), _s()), "ab_window_attention")
 
 
 def ln_mod_residual(y: torch.Tensor, *, scale=None, shift=None, residual=None, add_rows=None, out_f32=None,
                     out_bf16=None, eps: float = 1e-5, res_div: int = 1, res_mod: int = 0) -> None:
-    assert y.dtype == torch.bfloat16 and y.dim() == 2
+    assert y.dim() == 2
     rows, dim = y.shape
     a = AbLnModResidual()
     a.y = ptr(y)
+    a.in_dtype = _dt(y)
     a.ld_y = _ld(y)
     for t in (scale, shift):
         assert t is None or (t.dtype == torch.float32 and t.numel() == dim and t.is_contiguous())
@@ -293,11 +351,16 @@ def ln_mod_residual(y: torch.Tensor, *, scale=None, shift=None, residual=None, a
         assert out_f32.dtype == torch.float32 and out_f32.shape == (rows, dim)
         a.out_f32, a.ld_f32 = ptr(out_f32), _ld(out_f32)
     if out_bf16 is not None:
-        assert out_bf16.dtype == torch.bfloat16 and out_bf16.shape == (rows, dim)
+        assert out_bf16.shape == (rows, dim)
         a.out_bf16, a.ld_bf16 = ptr(out_bf16), _ld(out_bf16)
+        a.out_dtype = _dt(out_bf16)
     a.rows, a.dim, a.eps = rows, dim, eps
     a.res_div, a.res_mod = res_div, res_mod
-    check(lib().ab_ln_mod_residual(C.byref(a), _s()), "ab_ln_mod_residual")
+    nb = rows * dim * (2.0 + (4.0 if residual is not None and res_mod == 0 else 0.0)
+                       + (4.0 if out_f32 is not None else 0.0) + (2.0 if out_bf16 is not None else 0.0)
+                       + (4.0 if add_rows is not None else 0.0))
+    with _Timed("ln_mod_residual", nbytes=nb):
+        check(lib().ab_ln_mod_residual(C.byref(a), _s()), "ab_ln_mod_residual")
 
 
 def patch_merge_ln(x: torch.Tensor, gamma, beta, out: torch.Tensor, *, batch, c, h, w, d, eps=1e-5) -> None:
@@ -323,11 +386,12 @@ def perceiver_attention(q: torch.Tensor, kv: torch.Tensor, out: torch.Tensor, *,
     assert q.dtype == torch.float32 and q.is_contiguous() and q.dim() == 2
     lq, d = q.shape
     assert d == num_heads * head_dim
-    assert kv.dtype == torch.bfloat16 and kv.dim() == 2 and kv.shape[1] == 2 * d and kv.shape[0] % nloc == 0
+    assert kv.dim() == 2 and kv.shape[1] == 2 * d and kv.shape[0] % nloc == 0
     lk = kv.shape[0] // nloc
-    assert out.dtype == torch.bfloat16 and out.shape == (lq * nloc, d)
+    assert out.dtype == kv.dtype and out.shape == (lq * nloc, d)
     check(lib().ab_perceiver_attention(C.c_void_p(ptr(q)), C.c_void_p(ptr(kv)), C.c_void_p(ptr(out)),
-                                       C.c_int64(nloc), lq, lk, num_heads, head_dim, _ld(kv), _ld(out), _s()),
+                                       C.c_int64(nloc), lq, lk, num_heads, head_dim, _ld(kv), _ld(out), _dt(kv),
+                                       _s()),
           "ab_perceiver_attention")
 
 
@@ -345,9 +409,10 @@ def linear_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] 
 
 
 def patchify(fields: list, t_hist: int, h: int, w: int, p: int, out: torch.Tensor) -> None:
-    assert out.dtype == torch.bfloat16 and out.dim() == 2 and out.shape[0] == (h // p) * (w // p)
+    assert out.dim() == 2 and out.shape[0] == (h // p) * (w // p)
     arr = (AbFieldIn * len(fields))(*fields)
-    check(lib().ab_patchify(arr, len(fields), t_hist, h, w, p, C.c_void_p(ptr(out)), _ld(out), _s()), "ab_patchify")
+    check(lib().ab_patchify(arr, len(fields), t_hist, h, w, p, C.c_void_p(ptr(out)), _ld(out), _dt(out), _s()),
+          "ab_patchify")
 
 
 def unpatchify(fields: list, y: torch.Tensor, h: int, w: int, p: int) -> None:

@@ -42,8 +42,8 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                      uint32_t box_rows, uint32_t box_cols) {
+int make_tmap_16bit_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                       uint32_t box_rows, uint32_t box_cols, bool fp16) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
@@ -58,7 +58,7 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   cuuint64_t gstride[1] = {ld * 2};  // bytes, dims 1..rank-1
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estride[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+  CUresult r = fn(out, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -29,10 +29,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_tiled_fn();
 
-// 2D bf16 tensor map: inner dim = `cols` contiguous elements, outer dim = `rows` with `ld` elements
+// 2D bf16 / fp16 tensor map: inner dim = `cols` contiguous elements, outer dim = `rows` with `ld` elements
 // between rows; box = {box_cols, box_rows}; 128-byte swizzle; out-of-bounds reads return zero.
-int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                      uint32_t box_rows, uint32_t box_cols);
+int make_tmap_16bit_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                       uint32_t box_rows, uint32_t box_cols, bool fp16);
 
 #define AB_CHECK_ARG(cond, ...)            \
   do {                                     \

@@ -40,11 +40,12 @@ struct GemmArgs {
   const float* bias;
   const float* residual;
   float* out_f32;
-  __nv_bfloat16* out_bf16;
+  uint16_t* out_bf16;  // 16-bit output (bf16 or fp16, see out_half)
   int m, n, k;
   int ldr, ld_f32, ld_bf16;
   int act;
-  int vec_ok;  // all leading dimensions / pointers allow 16-byte vector access
+  int vec_ok;    // all leading dimensions / pointers allow 16-byte vector access
+  int out_half;  // 16-bit output is fp16 instead of bf16
 };
 
 template <int BN>
@@ -90,10 +91,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 p;
-        p.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-        p.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-        p.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-        p.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+        if (g.out_half) {
+          p.x = pack_f16x2(f[8 * j + 0], f[8 * j + 1]);
+          p.y = pack_f16x2(f[8 * j + 2], f[8 * j + 3]);
+          p.z = pack_f16x2(f[8 * j + 4], f[8 * j + 5]);
+          p.w = pack_f16x2(f[8 * j + 6], f[8 * j + 7]);
+        } else {
+          p.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+          p.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+          p.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+          p.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+        }
         o4[j] = p;
       }
     }
@@ -107,12 +115,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
       if (g.act == AB_ACT_GELU_ERF) x = gelu_erf(x);
       if (g.residual != nullptr) x += __ldg(g.residual + static_cast<size_t>(row) * g.ldr + col);
       if (g.out_f32 != nullptr) g.out_f32[static_cast<size_t>(row) * g.ld_f32 + col] = x;
-      if (g.out_bf16 != nullptr) g.out_bf16[static_cast<size_t>(row) * g.ld_bf16 + col] = __float2bfloat16_rn(x);
+      if (g.out_bf16 != nullptr) g.out_bf16[static_cast<size_t>(row) * g.ld_bf16 + col] = to16(x, g.out_half);
     }
   }
 }
 
-template <int BN>
+template <int BN, bool kHalfIn>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const GemmArgs g) {
@@ -177,7 +185,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(kBlockM, BN);
+      constexpr uint32_t idesc = umma_idesc_f16kind_f32(kBlockM, BN, kHalfIn);
       uint32_t it = 0, tc = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tc) {
         const uint32_t as = tc & 1u;
@@ -238,17 +246,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
-template <int BN>
+template <int BN, bool kHalfIn>
 static int launch_gemm(const AbGemm* p, const GemmArgs& args, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap ta, tw;
-  int rc = make_tmap_bf16_2d(&ta, p->a, p->m, p->k, p->lda, kBlockM, kBlockK);
+  int rc = make_tmap_16bit_2d(&ta, p->a, p->m, p->k, p->lda, kBlockM, kBlockK, kHalfIn);
   if (rc != AB_OK) return rc;
-  rc = make_tmap_bf16_2d(&tw, p->w, p->n, p->k, p->ldw, BN, kBlockK);
+  rc = make_tmap_16bit_2d(&tw, p->w, p->n, p->k, p->ldw, BN, kBlockK, kHalfIn);
   if (rc != AB_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, kHalfIn>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       set_error("ab_gemm_bf16: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes, cudaGetErrorString(e));
@@ -258,7 +266,7 @@ static int launch_gemm(const AbGemm* p, const GemmArgs& args, cudaStream_t strea
   }
   const long long tiles = ceil_div_ll(p->m, kBlockM) * ceil_div_ll(p->n, BN);
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
-  gemm_bf16_tn_kernel<BN><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tw, args);
+  gemm_bf16_tn_kernel<BN, kHalfIn><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tw, args);
   AB_COUNT_LAUNCH(1);
   AB_CHECK_LAUNCH("ab_gemm_bf16");
   return AB_OK;
@@ -276,6 +284,9 @@ extern "C" int ab_gemm_bf16(const AbGemm* p, void* stream) {
                "ab_gemm_bf16: K/lda/ldw must be multiples of 8 and ld >= K (k=%d lda=%d ldw=%d)", p->k, p->lda,
                p->ldw);
   AB_CHECK_ARG(p->act == AB_ACT_NONE || p->act == AB_ACT_GELU_ERF, "ab_gemm_bf16: unknown activation %d", p->act);
+  AB_CHECK_ARG((p->in_dtype == AB_DT_BF16 || p->in_dtype == AB_DT_F16) &&
+                   (p->out_dtype == AB_DT_BF16 || p->out_dtype == AB_DT_F16),
+               "ab_gemm_bf16: dtypes must be AB_DT_BF16 or AB_DT_F16");
   AB_CHECK_ARG(p->out_f32 == nullptr || p->ld_f32 >= p->n, "ab_gemm_bf16: ld_f32 < n");
   AB_CHECK_ARG(p->out_bf16 == nullptr || p->ld_bf16 >= p->n, "ab_gemm_bf16: ld_bf16 < n");
   AB_CHECK_ARG(p->residual == nullptr || p->ldr >= p->n, "ab_gemm_bf16: ldr < n");
@@ -284,7 +295,8 @@ extern "C" int ab_gemm_bf16(const AbGemm* p, void* stream) {
   a.bias = p->bias;
   a.residual = p->residual;
   a.out_f32 = p->out_f32;
-  a.out_bf16 = reinterpret_cast<__nv_bfloat16*>(p->out_bf16);
+  a.out_bf16 = reinterpret_cast<uint16_t*>(p->out_bf16);
+  a.out_half = p->out_dtype == AB_DT_F16;
   a.m = p->m;
   a.n = p->n;
   a.k = p->k;
@@ -298,7 +310,12 @@ extern "C" int ab_gemm_bf16(const AbGemm* p, void* stream) {
              (p->out_bf16 == nullptr || p->ld_bf16 % 8 == 0);
 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (p->n > 128) return launch_gemm<256>(p, a, s);
-  if (p->n > 64) return launch_gemm<128>(p, a, s);
-  return launch_gemm<64>(p, a, s);
+  if (p->in_dtype == AB_DT_F16) {
+    if (p->n > 128) return launch_gemm<256, true>(p, a, s);
+    if (p->n > 64) return launch_gemm<128, true>(p, a, s);
+    return launch_gemm<64, true>(p, a, s);
+  }
+  if (p->n > 128) return launch_gemm<256, false>(p, a, s);
+  if (p->n > 64) return launch_gemm<128, false>(p, a, s);
+  return launch_gemm<64, false>(p, a, s);
 }

@@ -16,9 +16,10 @@ namespace ab {
 
 struct PatchifyArgs {
   AbFieldIn f[AB_MAX_FIELDS];
-  __nv_bfloat16* out;
+  uint16_t* out;  // bf16 or fp16
   int nfields, t, h, w, p, ldk;
   int hp, wp;
+  int out_half;
 };
 
 __device__ __forceinline__ float transform_in(const AbFieldIn& f, float x) {
@@ -46,9 +47,9 @@ __global__ void __launch_bounds__(256) patchify_kernel(const __grid_constant__ P
   const int v = vt / a.t;
   const int ph = static_cast<int>(l / a.wp), pw = static_cast<int>(l % a.wp);
   const AbFieldIn& f = a.f[v];
-  __nv_bfloat16* o = a.out + l * a.ldk + static_cast<long long>(vt) * a.p * a.p;
+  uint16_t* o = a.out + l * a.ldk + static_cast<long long>(vt) * a.p * a.p;
   if (f.ptr == nullptr) {
-    const __nv_bfloat16 c = __float2bfloat16_rn(f.const_value);
+    const uint16_t c = to16(f.const_value, a.out_half);
     for (int i = 0; i < a.p * a.p; ++i) o[i] = c;
     return;
   }
@@ -58,8 +59,13 @@ __global__ void __launch_bounds__(256) patchify_kernel(const __grid_constant__ P
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const float4 x = __ldg(reinterpret_cast<const float4*>(base + static_cast<long long>(r) * a.w));
-      pk[r].x = pack_bf16x2(transform_in(f, x.x), transform_in(f, x.y));
-      pk[r].y = pack_bf16x2(transform_in(f, x.z), transform_in(f, x.w));
+      if (a.out_half) {
+        pk[r].x = pack_f16x2(transform_in(f, x.x), transform_in(f, x.y));
+        pk[r].y = pack_f16x2(transform_in(f, x.z), transform_in(f, x.w));
+      } else {
+        pk[r].x = pack_bf16x2(transform_in(f, x.x), transform_in(f, x.y));
+        pk[r].y = pack_bf16x2(transform_in(f, x.z), transform_in(f, x.w));
+      }
     }
     uint4* o4 = reinterpret_cast<uint4*>(o);  // 16 bf16 = 32 bytes; ldk % 8 == 0 and vt*16 keep alignment
     o4[0] = make_uint4(pk[0].x, pk[0].y, pk[1].x, pk[1].y);
@@ -67,7 +73,7 @@ __global__ void __launch_bounds__(256) patchify_kernel(const __grid_constant__ P
   } else {
     for (int r = 0; r < a.p; ++r)
       for (int c = 0; c < a.p; ++c)
-        o[r * a.p + c] = __float2bfloat16_rn(transform_in(f, __ldg(base + static_cast<long long>(r) * a.w + c)));
+        o[r * a.p + c] = to16(transform_in(f, __ldg(base + static_cast<long long>(r) * a.w + c)), a.out_half);
   }
 }
 
@@ -108,7 +114,7 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(const __grid_constant__
 }  // namespace ab
 
 extern "C" int ab_patchify(const AbFieldIn* fields, int32_t nfields, int32_t t, int32_t h, int32_t w, int32_t p,
-                           void* out_bf16, int32_t ldk, void* stream) {
+                           void* out_bf16, int32_t ldk, int32_t out_dtype, void* stream) {
   using namespace ab;
   AB_CHECK_ARG(fields && out_bf16, "ab_patchify: null argument");
   AB_CHECK_ARG(nfields > 0 && nfields <= AB_MAX_FIELDS, "ab_patchify: 1..%d fields supported (got %d)",
@@ -121,7 +127,9 @@ extern "C" int ab_patchify(const AbFieldIn* fields, int32_t nfields, int32_t t, 
     a.f[i] = fields[i];
     AB_CHECK_ARG(fields[i].ptr == nullptr || fields[i].scale != 0.f, "ab_patchify: zero scale for field %d", i);
   }
-  a.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  AB_CHECK_ARG(out_dtype == AB_DT_BF16 || out_dtype == AB_DT_F16, "ab_patchify: bad out_dtype");
+  a.out = reinterpret_cast<uint16_t*>(out_bf16);
+  a.out_half = out_dtype == AB_DT_F16;
   a.nfields = nfields;
   a.t = t;
   a.h = h;

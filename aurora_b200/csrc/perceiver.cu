@@ -13,8 +13,8 @@ namespace ab {
 
 struct PercArgs {
   const float* q;             // [Lq, D] f32
-  const __nv_bfloat16* kv;    // [Lk * nloc, 2D]  row = ck * nloc + loc ; columns [k | v]
-  __nv_bfloat16* out;         // [Lq * nloc, D]   row = cq * nloc + loc
+  const uint16_t* kv;         // [Lk * nloc, 2D]  row = ck * nloc + loc ; columns [k | v]  (bf16 or fp16)
+  uint16_t* out;              // [Lq * nloc, D]   row = cq * nloc + loc
   long long nloc;
   int lq, lk, heads, dh, dim;
   int ld_kv, ld_out;
@@ -23,7 +23,7 @@ struct PercArgs {
 
 // One thread per (location, query, head); head fastest so that a group of `heads` threads reads / writes
 // one full row contiguously.  kDH = head dim (32 or 64).
-template <int kDH>
+template <int kDH, int kHalf>
 __global__ void __launch_bounds__(256) perceiver_attention_kernel(const PercArgs a) {
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = a.nloc * a.lq * a.heads;
@@ -47,19 +47,16 @@ __global__ void __launch_bounds__(256) perceiver_attention_kernel(const PercArgs
   for (int i = 0; i < kDH; ++i) acc[i] = 0.f;
   float m = -INFINITY, l = 0.f;
   for (int c = 0; c < a.lk; ++c) {
-    const __nv_bfloat16* krow = a.kv + (static_cast<long long>(c) * a.nloc + loc) * a.ld_kv + h * kDH;
+    const uint16_t* krow = a.kv + (static_cast<long long>(c) * a.nloc + loc) * a.ld_kv + h * kDH;
     const uint4* kp = reinterpret_cast<const uint4*>(krow);
     const uint4* vp = reinterpret_cast<const uint4*>(krow + a.dim);
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < kDH / 8; ++i) {
-      const uint4 u = __ldg(kp + i);
-      const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&u);
+      float f[8];
+      unpack16x8<kHalf>(__ldg(kp + i), f);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(hp[j]);
-        s += q[8 * i + 2 * j] * f.x + q[8 * i + 2 * j + 1] * f.y;
-      }
+      for (int j = 0; j < 8; ++j) s += q[8 * i + j] * f[j];
     }
     const float mn = fmaxf(m, s);
     const float alpha = __expf(m - mn);
@@ -68,14 +65,10 @@ __global__ void __launch_bounds__(256) perceiver_attention_kernel(const PercArgs
     m = mn;
 #pragma unroll
     for (int i = 0; i < kDH / 8; ++i) {
-      const uint4 u = __ldg(vp + i);
-      const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&u);
+      float f[8];
+      unpack16x8<kHalf>(__ldg(vp + i), f);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(hp[j]);
-        acc[8 * i + 2 * j] = acc[8 * i + 2 * j] * alpha + p * f.x;
-        acc[8 * i + 2 * j + 1] = acc[8 * i + 2 * j + 1] * alpha + p * f.y;
-      }
+      for (int j = 0; j < 8; ++j) acc[8 * i + j] = acc[8 * i + j] * alpha + p * f[j];
     }
   }
   const float inv = 1.f / l;
@@ -83,10 +76,10 @@ __global__ void __launch_bounds__(256) perceiver_attention_kernel(const PercArgs
 #pragma unroll
   for (int i = 0; i < kDH / 8; ++i) {
     uint4 u;
-    u.x = pack_bf16x2(acc[8 * i] * inv, acc[8 * i + 1] * inv);
-    u.y = pack_bf16x2(acc[8 * i + 2] * inv, acc[8 * i + 3] * inv);
-    u.z = pack_bf16x2(acc[8 * i + 4] * inv, acc[8 * i + 5] * inv);
-    u.w = pack_bf16x2(acc[8 * i + 6] * inv, acc[8 * i + 7] * inv);
+    u.x = pack16x2<kHalf>(acc[8 * i] * inv, acc[8 * i + 1] * inv);
+    u.y = pack16x2<kHalf>(acc[8 * i + 2] * inv, acc[8 * i + 3] * inv);
+    u.z = pack16x2<kHalf>(acc[8 * i + 4] * inv, acc[8 * i + 5] * inv);
+    u.w = pack16x2<kHalf>(acc[8 * i + 6] * inv, acc[8 * i + 7] * inv);
     op[i] = u;
   }
 }
@@ -122,7 +115,7 @@ __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restri
 
 extern "C" int ab_perceiver_attention(const float* q, const void* kv_bf16, void* out_bf16, int64_t nloc, int32_t lq,
                                       int32_t lk, int32_t num_heads, int32_t head_dim, int32_t ld_kv,
-                                      int32_t ld_out, void* stream) {
+                                      int32_t ld_out, int32_t dtype, void* stream) {
   using namespace ab;
   AB_CHECK_ARG(q && kv_bf16 && out_bf16, "ab_perceiver_attention: null argument");
   AB_CHECK_ARG(head_dim == 32 || head_dim == 64, "ab_perceiver_attention: head_dim must be 32 or 64 (got %d)",
@@ -133,8 +126,9 @@ extern "C" int ab_perceiver_attention(const float* q, const void* kv_bf16, void*
                "ab_perceiver_attention: bad leading dimensions");
   PercArgs a;
   a.q = q;
-  a.kv = reinterpret_cast<const __nv_bfloat16*>(kv_bf16);
-  a.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  AB_CHECK_ARG(dtype == AB_DT_BF16 || dtype == AB_DT_F16, "ab_perceiver_attention: bad dtype");
+  a.kv = reinterpret_cast<const uint16_t*>(kv_bf16);
+  a.out = reinterpret_cast<uint16_t*>(out_bf16);
   a.nloc = nloc;
   a.lq = lq;
   a.lk = lk;
@@ -147,8 +141,13 @@ extern "C" int ab_perceiver_attention(const float* q, const void* kv_bf16, void*
   const long long total = nloc * lq * num_heads;
   const unsigned grid = static_cast<unsigned>(ceil_div_ll(total, 256));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (head_dim == 32) perceiver_attention_kernel<32><<<grid, 256, 0, s>>>(a);
-  else perceiver_attention_kernel<64><<<grid, 256, 0, s>>>(a);
+  if (head_dim == 32) {
+    if (dtype == AB_DT_F16) perceiver_attention_kernel<32, 1><<<grid, 256, 0, s>>>(a);
+    else perceiver_attention_kernel<32, 0><<<grid, 256, 0, s>>>(a);
+  } else {
+    if (dtype == AB_DT_F16) perceiver_attention_kernel<64, 1><<<grid, 256, 0, s>>>(a);
+    else perceiver_attention_kernel<64, 0><<<grid, 256, 0, s>>>(a);
+  }
   AB_COUNT_LAUNCH(1);
   AB_CHECK_LAUNCH("ab_perceiver_attention");
   return AB_OK;

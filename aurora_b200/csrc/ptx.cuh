@@ -4,6 +4,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -164,13 +165,13 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr_bytes) 
   return d;
 }
 
-// Instruction descriptor for kind::f16 with bf16 A/B (K-major both) and fp32 accumulation.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(uint32_t m, uint32_t n) {
-  return (1u << 4)            // D format: F32
-         | (1u << 7)          // A format: BF16
-         | (1u << 10)         // B format: BF16
-         | ((n >> 3) << 17)   // N / 8
-         | ((m >> 4) << 24);  // M / 16
+// Instruction descriptor for kind::f16 with bf16 (or fp16) A/B, K-major both, fp32 accumulation.
+__host__ __device__ constexpr uint32_t umma_idesc_f16kind_f32(uint32_t m, uint32_t n, bool fp16_operands) {
+  return (1u << 4)                              // D format: F32
+         | ((fp16_operands ? 0u : 1u) << 7)     // A format: F16 = 0, BF16 = 1
+         | ((fp16_operands ? 0u : 1u) << 10)    // B format
+         | ((n >> 3) << 17)                     // N / 8
+         | ((m >> 4) << 24);                    // M / 16
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread on behalf of the CTA.
@@ -214,6 +215,52 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  // saturating conversion: fp16 overflows at 65504 where bf16 would not
+  lo = fminf(fmaxf(lo, -65504.f), 65504.f);
+  hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// 16-bit storage types selected at run time: 0 = bf16 (the backbone, as the reference's autocast),
+// 1 = fp16 (encoder / decoder, which the reference keeps in fp32: 3 more mantissa bits at the same rate).
+template <int kHalf>
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
+  if constexpr (kHalf) return pack_f16x2(lo, hi);
+  else return pack_bf16x2(lo, hi);
+}
+template <int kHalf>
+__device__ __forceinline__ float2 unpack16x2(uint32_t u) {
+  if constexpr (kHalf) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+  else return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+}
+template <int kHalf>
+__device__ __forceinline__ void unpack16x8(const uint4& u, float (&f)[8]) {
+  float2 t;
+  t = unpack16x2<kHalf>(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack16x2<kHalf>(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack16x2<kHalf>(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack16x2<kHalf>(u.w); f[6] = t.x; f[7] = t.y;
+}
+template <int kHalf>
+__device__ __forceinline__ uint4 pack16x8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack16x2<kHalf>(f[0], f[1]);
+  u.y = pack16x2<kHalf>(f[2], f[3]);
+  u.z = pack16x2<kHalf>(f[4], f[5]);
+  u.w = pack16x2<kHalf>(f[6], f[7]);
+  return u;
+}
+__device__ __forceinline__ uint16_t to16(float x, int half) {
+  if (half) {
+    __half h = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+    return *reinterpret_cast<uint16_t*>(&h);
+  }
+  __nv_bfloat16 b = __float2bfloat16_rn(x);
+  return *reinterpret_cast<uint16_t*>(&b);
 }
 
 // Exact (erf-form) GELU, matching torch.nn.GELU() default.

@@ -40,13 +40,13 @@ __device__ __forceinline__ uint4 float8_to_bf16(const float (&f)[8]) {
 }
 
 struct LnArgs {
-  const __nv_bfloat16* y;  // [rows, ld_y]
+  const uint16_t* y;       // [rows, ld_y] bf16 or fp16
   const float* scale;      // [D] or null (=1)
   const float* shift;      // [D] or null (=0)
   const float* residual;   // [*, ld_res] or null
   const float* add_rows;   // [add_mod, D] or null
   float* out_f32;
-  __nv_bfloat16* out_bf16;
+  uint16_t* out_bf16;      // bf16 or fp16
   long long rows;
   int dim;
   int ld_y, ld_res, ld_f32, ld_bf16;
@@ -56,7 +56,7 @@ struct LnArgs {
 };
 
 // kChunks: 16-byte (8 x bf16) chunks cached per lane; D <= 256 * kChunks.
-template <int kChunks>
+template <int kChunks, int kHalfIn, int kHalfOut>
 __global__ void __launch_bounds__(kRowWarps * 32) ln_mod_residual_kernel(const LnArgs a) {
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) ln_mod_residual_kernel(const L
     const int ch = lane + c * 32;
     if (ch < nchunk) {
       uint4 u = __ldg(yrow + ch);
-      bf16x8_to_float(u, v[c]);
+      unpack16x8<kHalfIn>(u, v[c]);
 #pragma unroll
       for (int i = 0; i < 8; ++i) sum += v[c][i];
     } else {
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) ln_mod_residual_kernel(const L
         *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
         *reinterpret_cast<float4*>(p + 4) = make_float4(o[4], o[5], o[6], o[7]);
       }
-      if (a.out_bf16) *reinterpret_cast<uint4*>(a.out_bf16 + row * a.ld_bf16 + col) = float8_to_bf16(o);
+      if (a.out_bf16) *reinterpret_cast<uint4*>(a.out_bf16 + row * a.ld_bf16 + col) = pack16x8<kHalfOut>(o);
     }
   }
 }
@@ -263,8 +263,11 @@ __global__ void __launch_bounds__(kRowWarps * 32) patch_split_ln_kernel(const Sp
 extern "C" int ab_ln_mod_residual(const AbLnModResidual* p, void* stream) {
   using namespace ab;
   AB_CHECK_ARG(p && p->y, "ab_ln_mod_residual: null input");
-  AB_CHECK_ARG(p->rows > 0 && p->dim > 0 && p->dim % 8 == 0 && p->dim <= 4096,
-               "ab_ln_mod_residual: dim must be a multiple of 8 and <= 4096 (got %d)", p->dim);
+  AB_CHECK_ARG(p->rows > 0 && p->dim > 0 && p->dim % 8 == 0 && p->dim <= 2048,
+               "ab_ln_mod_residual: dim must be a multiple of 8 and <= 2048 (got %d)", p->dim);
+  AB_CHECK_ARG((p->in_dtype == AB_DT_BF16 || p->in_dtype == AB_DT_F16) &&
+                   (p->out_dtype == AB_DT_BF16 || p->out_dtype == AB_DT_F16),
+               "ab_ln_mod_residual: dtypes must be AB_DT_BF16 or AB_DT_F16");
   AB_CHECK_ARG(p->ld_y % 8 == 0 && (!p->residual || p->ld_res % 4 == 0) && (!p->out_f32 || p->ld_f32 % 4 == 0) &&
                    (!p->out_bf16 || p->ld_bf16 % 8 == 0),
                "ab_ln_mod_residual: leading dimensions must keep 16-byte alignment");
@@ -272,13 +275,13 @@ extern "C" int ab_ln_mod_residual(const AbLnModResidual* p, void* stream) {
   AB_CHECK_ARG(!p->add_rows || p->add_mod > 0, "ab_ln_mod_residual: add_rows needs add_mod > 0");
   AB_CHECK_ARG(p->res_mod == 0 || p->res_div > 0, "ab_ln_mod_residual: res_mod needs res_div > 0");
   LnArgs a;
-  a.y = reinterpret_cast<const __nv_bfloat16*>(p->y);
+  a.y = reinterpret_cast<const uint16_t*>(p->y);
   a.scale = p->scale;
   a.shift = p->shift;
   a.residual = p->residual;
   a.add_rows = p->add_rows;
   a.out_f32 = p->out_f32;
-  a.out_bf16 = reinterpret_cast<__nv_bfloat16*>(p->out_bf16);
+  a.out_bf16 = reinterpret_cast<uint16_t*>(p->out_bf16);
   a.rows = p->rows;
   a.dim = p->dim;
   a.ld_y = p->ld_y;
@@ -291,11 +294,19 @@ extern "C" int ab_ln_mod_residual(const AbLnModResidual* p, void* stream) {
   a.eps = p->eps;
   const unsigned grid = static_cast<unsigned>(ceil_div_ll(p->rows, kRowWarps));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (p->dim <= 256) ln_mod_residual_kernel<1><<<grid, kRowWarps * 32, 0, s>>>(a);
-  else if (p->dim <= 512) ln_mod_residual_kernel<2><<<grid, kRowWarps * 32, 0, s>>>(a);
-  else if (p->dim <= 1024) ln_mod_residual_kernel<4><<<grid, kRowWarps * 32, 0, s>>>(a);
-  else if (p->dim <= 2048) ln_mod_residual_kernel<8><<<grid, kRowWarps * 32, 0, s>>>(a);
-  else ln_mod_residual_kernel<16><<<grid, kRowWarps * 32, 0, s>>>(a);
+  const int hi = p->in_dtype == AB_DT_F16, ho = p->out_dtype == AB_DT_F16;
+#define AB_LN_LAUNCH(CH)                                                                              \
+  do {                                                                                                \
+    if (hi && ho) ln_mod_residual_kernel<CH, 1, 1><<<grid, kRowWarps * 32, 0, s>>>(a);                \
+    else if (hi) ln_mod_residual_kernel<CH, 1, 0><<<grid, kRowWarps * 32, 0, s>>>(a);                 \
+    else if (ho) ln_mod_residual_kernel<CH, 0, 1><<<grid, kRowWarps * 32, 0, s>>>(a);                 \
+    else ln_mod_residual_kernel<CH, 0, 0><<<grid, kRowWarps * 32, 0, s>>>(a);                         \
+  } while (0)
+  if (p->dim <= 256) AB_LN_LAUNCH(1);
+  else if (p->dim <= 512) AB_LN_LAUNCH(2);
+  else if (p->dim <= 1024) AB_LN_LAUNCH(4);
+  else AB_LN_LAUNCH(8);
+#undef AB_LN_LAUNCH
   AB_COUNT_LAUNCH(1);
   AB_CHECK_LAUNCH("ab_ln_mod_residual");
   return AB_OK;

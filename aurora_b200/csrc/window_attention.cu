@@ -289,6 +289,22 @@ extern "C" int ab_window_geometry(const int32_t res[3], const int32_t window[3],
   return AB_OK;
 }
 
+extern "C" int ab_window_index_map_host(const int32_t res[3], const int32_t window[3], const int32_t shift[3],
+                                        int32_t warped, int32_t* idx_out, uint8_t* group_out) {
+  using namespace ab;
+  AB_CHECK_ARG(res && window && shift && idx_out && group_out, "ab_window_index_map_host: null argument");
+  for (int a = 0; a < 3; ++a)
+    AB_CHECK_ARG(res[a] > 0 && window[a] > 0 && shift[a] >= 0 && shift[a] < window[a],
+                 "ab_window_index_map_host: bad res/window/shift on axis %d", a);
+  const WinGeom g = make_win_geom(res, window, shift, warped);
+  for (int i = 0; i < g.nwindows * g.ntok; ++i) {
+    int gr;
+    idx_out[i] = win_source_token(g, i / g.ntok, i % g.ntok, &gr);
+    group_out[i] = static_cast<uint8_t>(gr);
+  }
+  return AB_OK;
+}
+
 extern "C" int ab_window_index_map(const int32_t res[3], const int32_t window[3], const int32_t shift[3],
                                    int32_t warped, int32_t* idx_out, uint8_t* group_out, void* stream) {
   using namespace ab;

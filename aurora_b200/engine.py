@@ -60,7 +60,8 @@ def stage_resolutions(patch_res, n_stages):
 class AuroraEngine:
     """Runs `Aurora.forward` for one parameter set on one CUDA device."""
 
-    def __init__(self, cfg: ModelConfig, params: dict[str, torch.Tensor], variant: str = "base") -> None:
+    def __init__(self, cfg: ModelConfig, params: dict[str, torch.Tensor], variant: str = "base",
+                 edge_dtype: str = "fp16") -> None:
         self.cfg = cfg
         self.variant = variant
         some = next(iter(params.values()))
@@ -79,6 +80,10 @@ class AuroraEngine:
         if cfg.patch_size <= 0 or cfg.embed_dim % 8 != 0:
             raise ValueError("bad patch size / embedding dimension")
         cabi.lib()  # fail loudly now if the CUDA library is missing
+        # 16-bit operand types: backbone bf16 (the reference's autocast recipe), encoder / decoder fp16
+        # (the reference keeps them in fp32; fp16 has 3 more mantissa bits at the same tensor-core rate).
+        self.bb = torch.bfloat16
+        self.ed = torch.float16 if edge_dtype == "fp16" else torch.bfloat16
         self._w: dict = {}      # packed bf16 weights / fp32 vectors
         self._buf: dict = {}    # workspace
         self._lora: dict = {}   # lora index -> merged qkv/proj weights
@@ -96,12 +101,18 @@ class AuroraEngine:
         out += [(cfg.decoder_num_heads[i], cfg.embed_dim * 2 ** (n_dec - i - 1)) for i in range(n_dec)]
         return out
 
-    def _bf16(self, key: str) -> torch.Tensor:
-        t = self._w.get(("bf16", key))
+    def _w16(self, key: str, dtype: torch.dtype) -> torch.Tensor:
+        t = self._w.get((dtype, key))
         if t is None:
-            t = self.p[key].detach().to(torch.bfloat16).contiguous()
-            self._w[("bf16", key)] = t
+            t = self.p[key].detach().to(dtype).contiguous()
+            self._w[(dtype, key)] = t
         return t
+
+    def _bf16(self, key: str) -> torch.Tensor:
+        return self._w16(key, self.bb)
+
+    def _e16(self, key: str) -> torch.Tensor:
+        return self._w16(key, self.ed)
 
     def _f32(self, key: str) -> torch.Tensor:
         return self.p[key].detach().contiguous()
@@ -195,8 +206,8 @@ class AuroraEngine:
         if w is None:
             parts = [self.p[f"{prefix}.weights.{n}"].detach()[:, 0, :t].reshape(self.cfg.embed_dim, -1) for n in names]
             full = torch.cat(parts, dim=1)
-            wk = torch.zeros(full.shape[0], kpad, dtype=torch.bfloat16, device=self.device)
-            wk[:, : full.shape[1]] = full.to(torch.bfloat16)
+            wk = torch.zeros(full.shape[0], kpad, dtype=self.ed, device=self.device)
+            wk[:, : full.shape[1]] = full.to(self.ed)
             w = wk
             self._w[key] = w
         return w
@@ -322,20 +333,20 @@ class AuroraEngine:
         # surface patch embedding + level encoding + Perceiver-like MLP (encoder.py:286-288, 316-320)
         ks = len(fields_s) * t_hist * p * p
         ks_pad = _round_up(ks, 64)
-        a_s = self._buffer("enc.A_surf", (l, ks_pad), torch.bfloat16, zero=True)
+        a_s = self._buffer("enc.A_surf", (l, ks_pad), self.ed, zero=True)
         cabi.patchify(fields_s, t_hist, h, w, p, a_s)
         w_s = self._embed_weight("encoder.surf_token_embeds", names_s, t_hist, ks_pad)
         b_s = self._vec("enc.surf_bias", lambda: self._f32("encoder.surf_token_embeds.bias")
                         + self._f32("encoder.surf_level_encoding"))
         xs0 = self._buffer("enc.xs0", (l, d0), torch.float32)
-        xs0_b = self._buffer("enc.xs0_b", (l, d0), torch.bfloat16)
+        xs0_b = self._buffer("enc.xs0_b", (l, d0), self.ed)
         cabi.gemm(a_s, w_s, bias=b_s, out_f32=xs0, out_bf16=xs0_b)
         hid = int(d0 * cfg.mlp_ratio)
-        hbuf = self._buffer("enc.h", ((cfg.latent_levels - 1) * l, hid), torch.bfloat16)
-        mbuf = self._buffer("enc.m", ((cfg.latent_levels - 1) * l, d0), torch.bfloat16)
-        cabi.gemm(xs0_b, self._bf16("encoder.surf_mlp.net.0.weight"), bias=self._f32("encoder.surf_mlp.net.0.bias"),
+        hbuf = self._buffer("enc.h", ((cfg.latent_levels - 1) * l, hid), self.ed)
+        mbuf = self._buffer("enc.m", ((cfg.latent_levels - 1) * l, d0), self.ed)
+        cabi.gemm(xs0_b, self._e16("encoder.surf_mlp.net.0.weight"), bias=self._f32("encoder.surf_mlp.net.0.bias"),
                   out_bf16=hbuf[:l], act=GELU)
-        cabi.gemm(hbuf[:l], self._bf16("encoder.surf_mlp.net.2.weight"), bias=self._f32("encoder.surf_mlp.net.2.bias"),
+        cabi.gemm(hbuf[:l], self._e16("encoder.surf_mlp.net.2.weight"), bias=self._f32("encoder.surf_mlp.net.2.bias"),
                   out_bf16=mbuf[:l])
         # time embeddings (encoder.py:351-363); absolute time via datetime.timestamp() like the reference
         abs_h = torch.tensor([tm.timestamp() / 3600], dtype=torch.float32)
@@ -362,8 +373,8 @@ class AuroraEngine:
             bug_swap = (atmos_names_full.index("static_z"), atmos_names_full.index("z"))
         ka = len(atmos_names_full) * t_hist * p * p
         ka_pad = _round_up(ka, 64)
-        a_a = self._buffer("enc.A_atmos", (l, ka_pad), torch.bfloat16, zero=True)
-        xa = self._buffer("enc.xa", (n_lev * l, d0), torch.bfloat16)
+        a_a = self._buffer("enc.A_atmos", (l, ka_pad), self.ed, zero=True)
+        xa = self._buffer("enc.xa", (n_lev * l, d0), self.ed)
         lev = self._level_embeds(levels)
         per_level_stats = {k: atmos_stats_of(k, levels) for k in atmos_names}
         for ci, lvl in enumerate(levels):
@@ -388,24 +399,24 @@ class AuroraEngine:
         # ---- level aggregation: 3 shared latents attend over the levels, per location (encoder.py:173-196) ----
         nl = cfg.latent_levels - 1
         pre = "encoder.level_agg.layers.0"
-        kv = self._buffer("enc.kv", (n_lev * l, 2 * d0), torch.bfloat16)
-        cabi.gemm(xa, self._bf16(f"{pre}.0.to_kv.weight"), out_bf16=kv)
+        kv = self._buffer("enc.kv", (n_lev * l, 2 * d0), self.ed)
+        cabi.gemm(xa, self._e16(f"{pre}.0.to_kv.weight"), out_bf16=kv)
         if cfg.stabilise_level_agg:
             kview = kv[:, :d0]
             cabi.ln_mod_residual(kview, scale=self._f32(f"{pre}.0.ln_k.weight"), shift=self._f32(f"{pre}.0.ln_k.bias"),
                                  out_bf16=kview)
-        att = self._buffer("enc.att", (nl * l, d0), torch.bfloat16)
+        att = self._buffer("enc.att", (nl * l, d0), self.ed)
         cabi.perceiver_attention(self.enc_q, kv, att, nloc=l, num_heads=cfg.num_heads, head_dim=d0 // cfg.num_heads)
-        ao = self._buffer("enc.ao", (nl * l, d0), torch.bfloat16)
-        cabi.gemm(att, self._bf16(f"{pre}.0.to_out.weight"), out_bf16=ao)
+        ao = self._buffer("enc.ao", (nl * l, d0), self.ed)
+        cabi.gemm(att, self._e16(f"{pre}.0.to_out.weight"), out_bf16=ao)
         lat1 = self._buffer("enc.lat1", (nl * l, d0), torch.float32)
-        lat1_b = self._buffer("enc.lat1_b", (nl * l, d0), torch.bfloat16)
+        lat1_b = self._buffer("enc.lat1_b", (nl * l, d0), self.ed)
         cabi.ln_mod_residual(ao, scale=self._f32(f"{pre}.2.weight"), shift=self._f32(f"{pre}.2.bias"),
                              residual=self._f32("encoder.atmos_latents"), res_div=l, res_mod=nl,
                              out_f32=lat1, out_bf16=lat1_b, eps=cfg.perceiver_ln_eps)
-        cabi.gemm(lat1_b, self._bf16(f"{pre}.1.net.0.weight"), bias=self._f32(f"{pre}.1.net.0.bias"), out_bf16=hbuf,
+        cabi.gemm(lat1_b, self._e16(f"{pre}.1.net.0.weight"), bias=self._f32(f"{pre}.1.net.0.bias"), out_bf16=hbuf,
                   act=GELU)
-        cabi.gemm(hbuf, self._bf16(f"{pre}.1.net.2.weight"), bias=self._f32(f"{pre}.1.net.2.bias"), out_bf16=mbuf)
+        cabi.gemm(hbuf, self._e16(f"{pre}.1.net.2.weight"), bias=self._f32(f"{pre}.1.net.2.bias"), out_bf16=mbuf)
         cabi.ln_mod_residual(mbuf, scale=self._f32(f"{pre}.3.weight"),
                              shift=(self._f32(f"{pre}.3.bias") + tvec).contiguous(), residual=lat1, add_rows=posscale,
                              out_f32=x_f32[l:], out_bf16=x_b16[l:], eps=cfg.perceiver_ln_eps)
@@ -449,7 +460,7 @@ class AuroraEngine:
         all_res, padded = stage_resolutions(patch_res, n_enc)
         lora_idx = self._lora_index(rollout_step)
         l0 = x_f32.shape[0]
-        concat = self._buffer("bb.concat", (l0, 2 * d0), torch.bfloat16)
+        concat = self._buffer("bb.concat", (l0, 2 * d0), self.ed)  # decoder operand type
         skips: list[Optional[torch.Tensor]] = []
         cur_f, cur_b = x_f32, x_b16
         for i in range(n_enc):
@@ -520,22 +531,22 @@ class AuroraEngine:
         e = 2 * cfg.embed_dim
         n_lev = q.shape[0]
         pre = f"decoder.{name}.layers.0"
-        kv = self._buffer("dec.kv", (ctx.shape[0], 2 * e), torch.bfloat16)
-        cabi.gemm(ctx, self._bf16(f"{pre}.0.to_kv.weight"), out_bf16=kv)
-        att = self._buffer("dec.att", (n_lev * l, e), torch.bfloat16)
+        kv = self._buffer("dec.kv", (ctx.shape[0], 2 * e), self.ed)
+        cabi.gemm(ctx, self._e16(f"{pre}.0.to_kv.weight"), out_bf16=kv)
+        att = self._buffer("dec.att", (n_lev * l, e), self.ed)
         cabi.perceiver_attention(q, kv, att, nloc=l, num_heads=cfg.num_heads, head_dim=e // cfg.num_heads)
-        ao = self._buffer("dec.ao", (n_lev * l, e), torch.bfloat16)
-        cabi.gemm(att, self._bf16(f"{pre}.0.to_out.weight"), out_bf16=ao)
+        ao = self._buffer("dec.ao", (n_lev * l, e), self.ed)
+        cabi.gemm(att, self._e16(f"{pre}.0.to_out.weight"), out_bf16=ao)
         lat1 = self._buffer("dec.lat1", (n_lev * l, e), torch.float32)
-        lat1_b = self._buffer("dec.lat1_b", (n_lev * l, e), torch.bfloat16)
+        lat1_b = self._buffer("dec.lat1_b", (n_lev * l, e), self.ed)
         cabi.ln_mod_residual(ao, scale=self._f32(f"{pre}.2.weight"), shift=self._f32(f"{pre}.2.bias"), residual=lev_emb,
                              res_div=l, res_mod=n_lev, out_f32=lat1, out_bf16=lat1_b, eps=cfg.perceiver_ln_eps)
         hid = int(e * cfg.dec_mlp_ratio)
-        hbuf = self._buffer("dec.h", (n_lev * l, hid), torch.bfloat16)
-        cabi.gemm(lat1_b, self._bf16(f"{pre}.1.net.0.weight"), bias=self._f32(f"{pre}.1.net.0.bias"), out_bf16=hbuf,
+        hbuf = self._buffer("dec.h", (n_lev * l, hid), self.ed)
+        cabi.gemm(lat1_b, self._e16(f"{pre}.1.net.0.weight"), bias=self._f32(f"{pre}.1.net.0.bias"), out_bf16=hbuf,
                   act=GELU)
-        cabi.gemm(hbuf, self._bf16(f"{pre}.1.net.2.weight"), bias=self._f32(f"{pre}.1.net.2.bias"), out_bf16=ao)
-        out = self._buffer(f"dec.lat2.{tag}", (n_lev * l, e), torch.bfloat16)
+        cabi.gemm(hbuf, self._e16(f"{pre}.1.net.2.weight"), bias=self._f32(f"{pre}.1.net.2.bias"), out_bf16=ao)
+        out = self._buffer(f"dec.lat2.{tag}", (n_lev * l, e), self.ed)
         cabi.ln_mod_residual(ao, scale=self._f32(f"{pre}.3.weight"), shift=self._f32(f"{pre}.3.bias"), residual=lat1,
                              out_bf16=out, eps=cfg.perceiver_ln_eps)
         return out
@@ -551,7 +562,7 @@ class AuroraEngine:
             else:
                 ws = [self.p[f"decoder.{kind}.{n}.layers.{level}.weight"].detach() for n in names]
                 bs = [self.p[f"decoder.{kind}.{n}.layers.{level}.bias"].detach() for n in names]
-            w = (torch.cat(ws, 0).to(torch.bfloat16).contiguous(), torch.cat(bs, 0).float().contiguous())
+            w = (torch.cat(ws, 0).to(self.ed).contiguous(), torch.cat(bs, 0).float().contiguous())
             self._w[key] = w
         return w
 

@@ -50,7 +50,7 @@ class Aurora(nn.Module):
     _variant = "base"
 
     def __init__(self, *, surf_stats: Optional[dict[str, tuple[float, float]]] = None, autocast: bool = False,
-                 bf16_mode: bool = False, _init_seed: Optional[int] = None, **kw) -> None:
+                 bf16_mode: bool = False, _init_seed: Optional[int] = None, _init: str = "reference", **kw) -> None:
         super().__init__()
         if surf_stats:
             warnings.warn(
@@ -83,8 +83,12 @@ class Aurora(nn.Module):
         self.clamp_at_first_step = cfg.clamp_at_first_step
         self.autocast = autocast
 
-        for key, value in init_state_dict(cfg, seed=_init_seed, extra=self._extra_specs()).items():
-            self._put(key, value)
+        if _init == "empty":  # benchmarks fill the parameters themselves (on the device)
+            for key, shape, _kind in list(param_specs(cfg)) + list(self._extra_specs()):
+                self._put(key, torch.empty(shape, dtype=torch.float32))
+        else:
+            for key, value in init_state_dict(cfg, seed=_init_seed, extra=self._extra_specs()).items():
+                self._put(key, value)
         self._engine = None
         self._engine_sig = None
 

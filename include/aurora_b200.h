@@ -52,13 +52,18 @@ unsigned long long ab_launch_count(void);
  *
  *   out[m, n] = act( sum_k A[m, k] * W[n, k] + bias[n] ) + residual[m, n]
  *
- * A: bf16 [M, K] (lda), W: bf16 [N, K] (ldw; nn.Linear layout), fp32 accumulation in TMEM
+ * A: bf16|fp16 [M, K] (lda), W: same type [N, K] (ldw; nn.Linear layout), fp32 accumulation in TMEM
  * (tcgen05.mma kind::f16, TMA-staged 128B-swizzled operand tiles).  bias (f32 [N]) and residual
  * (f32 [M, ldr]) are optional (NULL).  act: AB_ACT_NONE or AB_ACT_GELU_ERF (exact erf GELU, as
  * nn.GELU()).  Either or both outputs may be requested: out_f32 [M, ld_f32], out_bf16 [M, ld_bf16].
  * Requirements: K % 8 == 0, lda % 8 == 0, ldw % 8 == 0, A/W 16-byte aligned.
  * ---------------------------------------------------------------------------------------------- */
 enum { AB_ACT_NONE = 0, AB_ACT_GELU_ERF = 1 };
+
+/* 16-bit storage / tensor-core operand types.  The Swin backbone uses bf16 (the reference's autocast
+ * recipe, aurora.py:327-343); encoder and decoder, which the reference keeps in fp32, use fp16 operands
+ * (11-bit mantissa, same tcgen05 rate, saturating stores) to stay closer to it. */
+enum { AB_DT_BF16 = 0, AB_DT_F16 = 1 };
 
 typedef struct AbGemm {
   const void* a;       /* bf16 [M, K] */
@@ -70,6 +75,8 @@ typedef struct AbGemm {
   int32_t m, n, k;
   int32_t lda, ldw, ldr, ld_f32, ld_bf16;
   int32_t act;
+  int32_t in_dtype;    /* AB_DT_*: type of a and w */
+  int32_t out_dtype;   /* AB_DT_*: type of the 16-bit output ("out_bf16") */
 } AbGemm;
 
 int ab_gemm_bf16(const AbGemm* g, void* stream);
@@ -118,6 +125,11 @@ int ab_window_geometry(const int32_t res[3], const int32_t window[3], const int3
 int ab_window_index_map(const int32_t res[3], const int32_t window[3], const int32_t shift[3], int32_t warped,
                         int32_t* idx_out, uint8_t* group_out, void* stream);
 
+/* The same function evaluated on the host (HOST pointers): the index arithmetic is one
+ * __host__ __device__ routine (csrc/window_index.cuh), so this pins it without a GPU. */
+int ab_window_index_map_host(const int32_t res[3], const int32_t window[3], const int32_t shift[3],
+                             int32_t warped, int32_t* idx_out, uint8_t* group_out);
+
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm + modulation + residual, one pass over the token stream:
  *
@@ -130,7 +142,7 @@ int ab_window_index_map(const int32_t res[3], const int32_t window[3], const int
  * time embeddings (encoder.py:320, 344-363: add_rows).  LN statistics in fp32, eps as given.
  * y: bf16 [rows, ld_y]; scale/shift: f32 [dim] or NULL (1 / 0); residual: f32 or NULL; res_mod == 0 means
  * rr = r.  Outputs: f32 and/or bf16, may alias `residual` (each row is read before it is written) and
- * out_bf16 may alias `y`.  dim % 8 == 0, dim <= 4096.
+ * out_bf16 may alias `y`.  dim % 8 == 0, dim <= 2048.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct AbLnModResidual {
   const void* y;
@@ -146,6 +158,8 @@ typedef struct AbLnModResidual {
   int32_t dim;
   int32_t ld_y, ld_res, ld_f32, ld_bf16;
   float eps;
+  int32_t in_dtype;   /* AB_DT_*: type of y */
+  int32_t out_dtype;  /* AB_DT_*: type of out_bf16 */
 } AbLnModResidual;
 
 int ab_ln_mod_residual(const AbLnModResidual* p, void* stream);
@@ -170,7 +184,7 @@ int ab_patch_split_ln(const void* y_bf16, const float* gamma, const float* beta,
  * per (location, head); head_dim 32 or 64. */
 int ab_perceiver_attention(const float* q, const void* kv_bf16, void* out_bf16, int64_t nloc, int32_t lq,
                            int32_t lk, int32_t num_heads, int32_t head_dim, int32_t ld_kv, int32_t ld_out,
-                           void* stream);
+                           int32_t dtype /* AB_DT_* of kv and out */, void* stream);
 
 /* y f32 [rows, n] = silu_out?( silu_in?(x f32 [rows, k]) W^T + bias ), W f32 [n, k]: the handful of
  * location-independent vectors (time MLP swin3d.py:805-809,914; adaLN modulation film.py:27-28; level,
@@ -198,7 +212,7 @@ typedef struct AbFieldIn {
  * pixel (hp*p + p1, wp*p + p2)); columns >= nfields*t_hist*p*p are left untouched (keep them zero).
  * Replaces Batch.normalise + torch.stack (encoder.py:213-215) + conv3d im2col (patchembed.py:100-112). */
 int ab_patchify(const AbFieldIn* fields, int32_t nfields, int32_t t_hist, int32_t h, int32_t w, int32_t p,
-                void* out_bf16, int32_t ldk, void* stream);
+                void* out_bf16, int32_t ldk, int32_t out_dtype /* AB_DT_* */, void* stream);
 
 typedef struct AbFieldOut {
   float* ptr;         /* (H, W) output plane, physical units */
