@@ -280,7 +280,8 @@ def test_patchify_matches_im2col(p, h, w):
     x = torch.stack(planes, 0)  # (V, T, H, W)
     ref = x.view(nv + 1, t, h // p, p, w // p, p).permute(2, 4, 0, 1, 3, 5).reshape((h // p) * (w // p), k)
     torch.testing.assert_close(out[:, :k].float(), ref, rtol=1e-2, atol=1e-2)
-    assert out[:, k:].abs().max().item() == 0
+    if kpad > k:
+        assert out[:, k:].abs().max().item() == 0
 
 
 @pytest.mark.parametrize("p,h,w", [(4, 32, 64), (3, 45, 90)])
