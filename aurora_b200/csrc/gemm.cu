@@ -31,7 +31,8 @@ struct GemmCfg {
   static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr uint32_t kTmemCols = 2 * BN;  // two accumulator stages
   static constexpr int kBarrierBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + 1024;  // +1024: manual alignment
+  static constexpr int kStagingBytes = kNumEpiWarps * 4096;  // one 32-row x 128-byte store box per epilogue warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024;  // +1024: alignment
   static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols >= 32 && kTmemCols <= 512, "TMEM columns");
   static_assert((2 * kStages + 4) * 8 + 4 <= kBarrierBytes, "barrier area");
 };
@@ -46,6 +47,7 @@ struct GemmArgs {
   int act;
   int vec_ok;    // all leading dimensions / pointers allow 16-byte vector access
   int out_half;  // 16-bit output is fp16 instead of bf16
+  int tma_out;   // 16-bit-only output written through swizzled smem + TMA store (tmap_out valid)
 };
 
 template <int BN>
@@ -120,17 +122,67 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
   }
 }
 
+// Bias / activation on 32 accumulator columns of one row, converted to 16 bit and written as four 16-byte
+// chunks into the warp's staging box (row = lane, 128 bytes per row, 128B swizzle: chunk ^= row & 7, the
+// layout a CU_TENSOR_MAP_SWIZZLE_128B store expects).  `chunk0` = 0 or 4 (first / second 32 columns).
+template <int BN>
+__device__ __forceinline__ void epilogue_stage_half(const GemmArgs& g, const uint32_t (&v)[32], int col0,
+                                                    uint32_t stage_row, int lane, int chunk0) {
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  if (g.bias != nullptr) {
+    if (col0 + 32 <= g.n) {
+      const float4* b4 = reinterpret_cast<const float4*>(g.bias + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(b4 + j);
+        f[4 * j + 0] += b.x;
+        f[4 * j + 1] += b.y;
+        f[4 * j + 2] += b.z;
+        f[4 * j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < g.n) f[j] += __ldg(g.bias + col0 + j);
+    }
+  }
+  if (g.act == AB_ACT_GELU_ERF) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t p0, p1, p2, p3;
+    if (g.out_half) {
+      p0 = pack_f16x2(f[8 * j + 0], f[8 * j + 1]);
+      p1 = pack_f16x2(f[8 * j + 2], f[8 * j + 3]);
+      p2 = pack_f16x2(f[8 * j + 4], f[8 * j + 5]);
+      p3 = pack_f16x2(f[8 * j + 6], f[8 * j + 7]);
+    } else {
+      p0 = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+      p1 = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+      p2 = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+      p3 = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+    }
+    const uint32_t addr = stage_row + (((chunk0 + j) ^ (lane & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+  }
+}
+
 template <int BN, bool kHalfIn>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                    const GemmArgs g) {
+                    const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024-byte alignment.
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kStageBytesA;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* smem_stage_out = smem + Cfg::kStages * Cfg::kStageBytes;  // 1024-byte aligned (stages are)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stage_out + Cfg::kStagingBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -142,6 +194,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_w);
+    if (g.tma_out) prefetch_tmap(&tmap_out);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -224,12 +277,38 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_wait(&tmem_full_bar[as], aph);
       tc_fence_after_sync();
       const int row = m0 + q * 32 + lane;
+      if (g.tma_out) {
+        // 16-bit output: TMEM -> registers -> 128B-swizzled smem box {64 cols x 32 rows} -> TMA store.
+        // Stores are full 128-byte rows and asynchronous; M / N tails are clipped by the tensor map.
+        uint8_t* stage = smem_stage_out + (warp - 4) * 4096;
+        const uint32_t stage_row = smem_u32(stage) + lane * 128;
 #pragma unroll 1
-      for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c, v);
-        tmem_ld_wait();
-        epilogue_chunk<BN>(g, v, row, n0 + c);
+        for (int c = half * 64; c < BN; c += 128) {  // 64-column boxes, interleaved between the two warp sets
+          if (n0 + c >= g.n) break;                   // warp-uniform
+          uint32_t v0[32], v1[32];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c;
+          tmem_ld_32x32b_x32(taddr, v0);
+          tmem_ld_32x32b_x32(taddr + 32, v1);
+          tmem_ld_wait();
+          if (lane == 0) tma_store_wait_read<0>();  // previous box of this warp has left the staging buffer
+          __syncwarp();
+          epilogue_stage_half<BN>(g, v0, n0 + c, stage_row, lane, 0);
+          epilogue_stage_half<BN>(g, v1, n0 + c + 32, stage_row, lane, 4);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_out, stage, n0 + c, m0 + q * 32);
+            tma_store_commit();
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c, v);
+          tmem_ld_wait();
+          epilogue_chunk<BN>(g, v, row, n0 + c);
+        }
       }
       tc_fence_before_sync();
       __syncwarp();
@@ -237,6 +316,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   }
 
+  if (warp >= 4 && g.tma_out && lane == 0) tma_store_wait_all<0>();  // smem must outlive the bulk stores
   __syncwarp();
   tc_fence_before_sync();
   __syncthreads();
@@ -254,6 +334,11 @@ static int launch_gemm(const AbGemm* p, const GemmArgs& args, cudaStream_t strea
   if (rc != AB_OK) return rc;
   rc = make_tmap_16bit_2d(&tw, p->w, p->n, p->k, p->ldw, BN, kBlockK, kHalfIn);
   if (rc != AB_OK) return rc;
+  CUtensorMap tout = ta;  // placeholder when unused
+  if (args.tma_out) {
+    rc = make_tmap_16bit_2d(&tout, p->out_bf16, p->m, p->n, p->ld_bf16, 32, 64, args.out_half != 0);
+    if (rc != AB_OK) return rc;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, kHalfIn>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -266,7 +351,7 @@ static int launch_gemm(const AbGemm* p, const GemmArgs& args, cudaStream_t strea
   }
   const long long tiles = ceil_div_ll(p->m, kBlockM) * ceil_div_ll(p->n, BN);
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
-  gemm_bf16_tn_kernel<BN, kHalfIn><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tw, args);
+  gemm_bf16_tn_kernel<BN, kHalfIn><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tw, tout, args);
   AB_COUNT_LAUNCH(1);
   AB_CHECK_LAUNCH("ab_gemm_bf16");
   return AB_OK;
@@ -309,6 +394,9 @@ extern "C" int ab_gemm_bf16(const AbGemm* p, void* stream) {
              (p->residual == nullptr || p->ldr % 4 == 0) && (p->out_f32 == nullptr || p->ld_f32 % 4 == 0) &&
              (p->out_bf16 == nullptr || p->ld_bf16 % 8 == 0);
 
+  // TMA-store epilogue: 16-bit output only, no residual, 16-byte aligned rows.
+  a.tma_out = p->out_bf16 != nullptr && p->out_f32 == nullptr && p->residual == nullptr && al16(p->out_bf16) &&
+              p->ld_bf16 % 8 == 0 && (p->bias == nullptr || (reinterpret_cast<uintptr_t>(p->bias) & 15u) == 0);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (p->in_dtype == AB_DT_F16) {
     if (p->n > 128) return launch_gemm<256, true>(p, a, s);

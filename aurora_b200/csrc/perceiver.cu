@@ -21,66 +21,85 @@ struct PercArgs {
   float scale;
 };
 
-// One thread per (location, query, head); head fastest so that a group of `heads` threads reads / writes
-// one full row contiguously.  kDH = head dim (32 or 64).
-template <int kDH, int kHalf>
+// One warp per (location, query): lane l owns features [l*E, (l+1)*E) of the D-wide row (E = D/32), i.e. a
+// 1/lanes_per_head slice of one head; partial dot products are reduced over the lanes of a head with
+// xor-shuffles, the softmax over the (<= 16) keys is online.  Every K / V / output row is therefore read or
+// written by one warp as one contiguous, fully coalesced line.
+template <int E, int kHalf>
 __global__ void __launch_bounds__(256) perceiver_attention_kernel(const PercArgs a) {
-  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = a.nloc * a.lq * a.heads;
-  if (gid >= total) return;
-  const int h = static_cast<int>(gid % a.heads);
-  long long t = gid / a.heads;
-  const int iq = static_cast<int>(t % a.lq);
-  const long long loc = t / a.lq;
-  float q[kDH];
-  const float4* qp = reinterpret_cast<const float4*>(a.q + static_cast<long long>(iq) * a.dim + h * kDH);
+  const long long wid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = a.nloc * a.lq;
+  if (wid >= total) return;
+  const int iq = static_cast<int>(wid % a.lq);  // queries of one location are adjacent: K/V rows stay in L1/L2
+  const long long loc = wid / a.lq;
+  const int lanes_per_head = a.dh / E;
+  float q[E];
+  {
+    const float* qp = a.q + static_cast<long long>(iq) * a.dim + lane * E;
 #pragma unroll
-  for (int i = 0; i < kDH / 4; ++i) {
-    const float4 v = __ldg(qp + i);
-    q[4 * i] = v.x * a.scale;
-    q[4 * i + 1] = v.y * a.scale;
-    q[4 * i + 2] = v.z * a.scale;
-    q[4 * i + 3] = v.w * a.scale;
+    for (int i = 0; i < E; i += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(qp + i));
+      q[i] = v.x * a.scale;
+      q[i + 1] = v.y * a.scale;
+      q[i + 2] = v.z * a.scale;
+      q[i + 3] = v.w * a.scale;
+    }
   }
-  float acc[kDH];
+  float acc[E];
 #pragma unroll
-  for (int i = 0; i < kDH; ++i) acc[i] = 0.f;
+  for (int i = 0; i < E; ++i) acc[i] = 0.f;
   float m = -INFINITY, l = 0.f;
   for (int c = 0; c < a.lk; ++c) {
-    const uint16_t* krow = a.kv + (static_cast<long long>(c) * a.nloc + loc) * a.ld_kv + h * kDH;
-    const uint4* kp = reinterpret_cast<const uint4*>(krow);
-    const uint4* vp = reinterpret_cast<const uint4*>(krow + a.dim);
-    float s = 0.f;
+    const uint16_t* krow = a.kv + (static_cast<long long>(c) * a.nloc + loc) * a.ld_kv + lane * E;
+    float kf[E], vf[E];
+    if constexpr (E >= 8) {
 #pragma unroll
-    for (int i = 0; i < kDH / 8; ++i) {
-      float f[8];
-      unpack16x8<kHalf>(__ldg(kp + i), f);
+      for (int i = 0; i < E / 8; ++i) {
+        float t[8];
+        unpack16x8<kHalf>(__ldg(reinterpret_cast<const uint4*>(krow) + i), t);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += q[8 * i + j] * f[j];
+        for (int j = 0; j < 8; ++j) kf[8 * i + j] = t[j];
+        unpack16x8<kHalf>(__ldg(reinterpret_cast<const uint4*>(krow + a.dim) + i), t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) vf[8 * i + j] = t[j];
+      }
+    } else {
+      const uint2 ku = __ldg(reinterpret_cast<const uint2*>(krow));
+      const uint2 vu = __ldg(reinterpret_cast<const uint2*>(krow + a.dim));
+      float2 t;
+      t = unpack16x2<kHalf>(ku.x); kf[0] = t.x; kf[1] = t.y;
+      t = unpack16x2<kHalf>(ku.y); kf[2] = t.x; kf[3] = t.y;
+      t = unpack16x2<kHalf>(vu.x); vf[0] = t.x; vf[1] = t.y;
+      t = unpack16x2<kHalf>(vu.y); vf[2] = t.x; vf[3] = t.y;
     }
-    const float mn = fmaxf(m, s);
+    float sdot = 0.f;
+#pragma unroll
+    for (int i = 0; i < E; ++i) sdot = fmaf(q[i], kf[i], sdot);
+    for (int o = 1; o < lanes_per_head; o <<= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
+    const float mn = fmaxf(m, sdot);
     const float alpha = __expf(m - mn);
-    const float p = __expf(s - mn);
+    const float p = __expf(sdot - mn);
     l = l * alpha + p;
     m = mn;
 #pragma unroll
-    for (int i = 0; i < kDH / 8; ++i) {
-      float f[8];
-      unpack16x8<kHalf>(__ldg(vp + i), f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[8 * i + j] = acc[8 * i + j] * alpha + p * f[j];
-    }
+    for (int i = 0; i < E; ++i) acc[i] = fmaf(p, vf[i], acc[i] * alpha);
   }
   const float inv = 1.f / l;
-  uint4* op = reinterpret_cast<uint4*>(a.out + (static_cast<long long>(iq) * a.nloc + loc) * a.ld_out + h * kDH);
+  uint16_t* orow = a.out + (static_cast<long long>(iq) * a.nloc + loc) * a.ld_out + lane * E;
+  if constexpr (E >= 8) {
 #pragma unroll
-  for (int i = 0; i < kDH / 8; ++i) {
-    uint4 u;
-    u.x = pack16x2<kHalf>(acc[8 * i] * inv, acc[8 * i + 1] * inv);
-    u.y = pack16x2<kHalf>(acc[8 * i + 2] * inv, acc[8 * i + 3] * inv);
-    u.z = pack16x2<kHalf>(acc[8 * i + 4] * inv, acc[8 * i + 5] * inv);
-    u.w = pack16x2<kHalf>(acc[8 * i + 6] * inv, acc[8 * i + 7] * inv);
-    op[i] = u;
+    for (int i = 0; i < E / 8; ++i) {
+      float t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = acc[8 * i + j] * inv;
+      reinterpret_cast<uint4*>(orow)[i] = pack16x8<kHalf>(t);
+    }
+  } else {
+    uint2 u;
+    u.x = pack16x2<kHalf>(acc[0] * inv, acc[1] * inv);
+    u.y = pack16x2<kHalf>(acc[2] * inv, acc[3] * inv);
+    *reinterpret_cast<uint2*>(orow) = u;
   }
 }
 
@@ -138,16 +157,25 @@ extern "C" int ab_perceiver_attention(const float* q, const void* kv_bf16, void*
   a.ld_kv = ld_kv;
   a.ld_out = ld_out;
   a.scale = 1.0f / sqrtf(static_cast<float>(head_dim));
-  const long long total = nloc * lq * num_heads;
-  const unsigned grid = static_cast<unsigned>(ceil_div_ll(total, 256));
+  const int e = dim / 32;
+  AB_CHECK_ARG(dim % 32 == 0 && (e == 4 || e == 8 || e == 16 || e == 32) && head_dim % e == 0 &&
+                   ((head_dim / e) & (head_dim / e - 1)) == 0,
+               "ab_perceiver_attention: unsupported width (dim=%d head_dim=%d): need dim/32 in {4,8,16,32} dividing "
+               "head_dim by a power of two", dim, head_dim);
+  const long long total = nloc * lq;  // warps
+  const unsigned grid = static_cast<unsigned>(ceil_div_ll(total * 32, 256));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (head_dim == 32) {
-    if (dtype == AB_DT_F16) perceiver_attention_kernel<32, 1><<<grid, 256, 0, s>>>(a);
-    else perceiver_attention_kernel<32, 0><<<grid, 256, 0, s>>>(a);
-  } else {
-    if (dtype == AB_DT_F16) perceiver_attention_kernel<64, 1><<<grid, 256, 0, s>>>(a);
-    else perceiver_attention_kernel<64, 0><<<grid, 256, 0, s>>>(a);
-  }
+  const bool hf = dtype == AB_DT_F16;
+#define AB_PERC(EE)                                                          \
+  do {                                                                       \
+    if (hf) perceiver_attention_kernel<EE, 1><<<grid, 256, 0, s>>>(a);       \
+    else perceiver_attention_kernel<EE, 0><<<grid, 256, 0, s>>>(a);          \
+  } while (0)
+  if (e == 4) AB_PERC(4);
+  else if (e == 8) AB_PERC(8);
+  else if (e == 16) AB_PERC(16);
+  else AB_PERC(32);
+#undef AB_PERC
   AB_COUNT_LAUNCH(1);
   AB_CHECK_LAUNCH("ab_perceiver_attention");
   return AB_OK;

@@ -61,6 +61,12 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Byte offset of 16-byte chunk `chunk` (0..7) of row `row` in a [rows][128 B] XOR-swizzled tile.
 __device__ __forceinline__ uint32_t swz(int row, int chunk) {
   return static_cast<uint32_t>(row * kRowBytes + ((chunk ^ (row & 7)) << 4));
@@ -90,14 +96,21 @@ __global__ void __launch_bounds__(kAttnThreads, 2) window_attention_kernel(const
   const int ld = 3 * a.dim;
 
   // ---- 1. index map + gather -------------------------------------------------------------------
+  int grp0 = 0;
+  win_source_token(g, win, 0, &grp0);
+  int differs = 0;
   for (int t = tid; t < npad; t += kAttnThreads) {
     int grp = kPadGroup;
     int src = -2;  // rows in [ntok, npad): not part of the window at all
-    if (t < ntok) src = win_source_token(g, win, t, &grp);
+    if (t < ntok) {
+      src = win_source_token(g, win, t, &grp);
+      differs |= (grp != grp0);
+    }
     sSrc[t] = src;
     sGrp[t] = static_cast<uint8_t>(grp);
   }
-  __syncthreads();
+  // Most windows of a shifted block hold a single group: the mask is then all zeros and is skipped.
+  const bool masked = __syncthreads_or(differs) != 0 && g.shifted;
   {
     const uint32_t sq = smem_u32(sQ), sk = smem_u32(sK), sv = smem_u32(sV);
     // 8 lanes move one 128-byte row of q, k and v each.
@@ -137,17 +150,26 @@ __global__ void __launch_bounds__(kAttnThreads, 2) window_attention_kernel(const
     for (int kk = 0; kk < 4; ++kk)
       ldsm_x4(sq + swz(r0 + (lane & 15), kk * 2 + (lane >> 4)), qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3]);
 
+    // 1/sqrt(64) = 2^-3 is exact in bf16: fold it into the Q fragments once.
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&qf[kk][r]);
+        v = __hmul2(v, __float2bfloat162_rn(0.125f));
+        qf[kk][r] = *reinterpret_cast<uint32_t*>(&v);
+      }
+
     const int qrow0 = r0 + (lane >> 2);  // this thread's two query rows: qrow0, qrow0 + 8
     const int qrow1 = qrow0 + 8;
     const int gq0 = sGrp[qrow0], gq1 = sGrp[qrow1];
     constexpr float kLog2e = 1.4426950408889634f;
-    constexpr float kScale = 0.125f * kLog2e;  // 1/sqrt(64), in the exp2 domain
-    constexpr float kMasked = -100.0f * kLog2e;
+    const bool ragged = ntok != npad;
 
     float o[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;  // running max (logit domain) and sum
 
     for (int kb = 0; kb < npad; kb += kKeyBlock) {
       float s[6][4];
@@ -166,43 +188,58 @@ __global__ void __launch_bounds__(kAttnThreads, 2) window_attention_kernel(const
           }
         }
       }
-      // scale, mask, optional bias; running max
+      const int kcol = kb + (lane & 3) * 2;  // this thread's first key column inside tile j: kcol + 8 j
+      if (a.bias != nullptr) {  // optional dense additive bias (never set by Aurora checkpoints)
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int key = kcol + j * 8 + (e & 1), qrow = (e < 2) ? qrow0 : qrow1;
+            if (key < ntok && qrow < ntok)
+              s[j][e] += __ldg(a.bias + (static_cast<size_t>(head) * ntok + qrow) * ntok + key);
+          }
+      }
+      if (masked) {  // shifted-window mask from one byte of group id per token (0 / -100, swin3d.py:357-358)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const int key = kcol + j * 8;
+          if (key < npad) {
+            const uint16_t gk2 = *reinterpret_cast<const uint16_t*>(sGrp + key);  // two adjacent keys
+            const int gk_a = gk2 & 0xff, gk_b = gk2 >> 8;
+            if (gk_a != gq0) s[j][0] -= 100.f;
+            if (gk_b != gq0) s[j][1] -= 100.f;
+            if (gk_a != gq1) s[j][2] -= 100.f;
+            if (gk_b != gq1) s[j][3] -= 100.f;
+          }
+        }
+      }
+      if (ragged || kb + kKeyBlock > npad) {  // key columns past the window (clamped windows / last block)
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (kcol + j * 8 + (e & 1) >= ntok) s[j][e] = -INFINITY;
+      }
       float mx0 = m0, mx1 = m1;
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int key = kb + j * 8 + (lane & 3) * 2 + (e & 1);
-          const int qrow = (e < 2) ? qrow0 : qrow1;
-          float v = s[j][e] * kScale;
-          if (key >= ntok) {
-            v = -INFINITY;
-          } else {
-            if (a.bias != nullptr && qrow < ntok)
-              v += kLog2e * __ldg(a.bias + (static_cast<size_t>(head) * ntok + qrow) * ntok + key);
-            if (g.shifted) {
-              const int gk = sGrp[key];
-              if (gk != ((e < 2) ? gq0 : gq1)) v += kMasked;
-            }
-          }
-          s[j][e] = v;
-          if (e < 2) mx0 = fmaxf(mx0, v);
-          else mx1 = fmaxf(mx1, v);
-        }
+        mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
       }
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      const float alpha0 = exp2f(m0 - mx0), alpha1 = exp2f(m1 - mx1);
+      const float alpha0 = ex2_approx((m0 - mx0) * kLog2e), alpha1 = ex2_approx((m1 - mx1) * kLog2e);
       m0 = mx0;
       m1 = mx1;
+      const float nm0 = -mx0 * kLog2e, nm1 = -mx1 * kLog2e;
       float sum0 = 0.f, sum1 = 0.f;
       uint32_t pf[3][4];
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
-        const float p0 = exp2f(s[j][0] - m0), p1 = exp2f(s[j][1] - m0);
-        const float p2 = exp2f(s[j][2] - m1), p3 = exp2f(s[j][3] - m1);
+        const float p0 = ex2_approx(fmaf(s[j][0], kLog2e, nm0)), p1 = ex2_approx(fmaf(s[j][1], kLog2e, nm0));
+        const float p2 = ex2_approx(fmaf(s[j][2], kLog2e, nm1)), p3 = ex2_approx(fmaf(s[j][3], kLog2e, nm1));
         sum0 += p0 + p1;
         sum1 += p2 + p3;
         pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
