@@ -72,74 +72,109 @@ __device__ __forceinline__ uint32_t swz(int row, int chunk) {
   return static_cast<uint32_t>(row * kRowBytes + ((chunk ^ (row & 7)) << 4));
 }
 
+struct AttnItem {
+  int head, win, b;
+};
+
+__device__ __forceinline__ AttnItem decode_item(const AttnArgs& a, long long item) {
+  AttnItem it;
+  it.head = static_cast<int>(item % a.num_heads);
+  item /= a.num_heads;
+  it.win = static_cast<int>(item % a.g.nwindows);
+  it.b = static_cast<int>(item / a.g.nwindows);
+  return it;
+}
+
+// Persistent CTAs (two per SM), two shared-memory buffers each: while the nine warps run the attention
+// math of item i out of buffer i&1, the cp.async gather of item i+1 is already in flight into the other.
 __global__ void __launch_bounds__(kAttnThreads, 2) window_attention_kernel(const AttnArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const WinGeom& g = a.g;
   const int ntok = g.ntok;
   const int npad = (ntok + 15) & ~15;
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + npad * kRowBytes;
-  uint8_t* sV = sK + npad * kRowBytes;
-  int* sSrc = reinterpret_cast<int*>(sV + npad * kRowBytes);
-  uint8_t* sGrp = reinterpret_cast<uint8_t*>(sSrc + npad);
+  const int tile_bytes = npad * kRowBytes;
+  const int buf_bytes = 3 * tile_bytes + npad * static_cast<int>(sizeof(int)) + npad;
+  const int buf_stride = (buf_bytes + 127) & ~127;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-
-  int item = blockIdx.x;
-  const int head = item % a.num_heads;
-  item /= a.num_heads;
-  const int win = item % g.nwindows;
-  const int b = item / g.nwindows;
-  const long long row_base = static_cast<long long>(b) * a.tokens_per_batch;
   const int ld = 3 * a.dim;
+  const long long n_items = static_cast<long long>(a.batch) * g.nwindows * a.num_heads;
 
-  // ---- 1. index map + gather -------------------------------------------------------------------
-  int grp0 = 0;
-  win_source_token(g, win, 0, &grp0);
-  int differs = 0;
-  for (int t = tid; t < npad; t += kAttnThreads) {
-    int grp = kPadGroup;
-    int src = -2;  // rows in [ntok, npad): not part of the window at all
-    if (t < ntok) {
-      src = win_source_token(g, win, t, &grp);
-      differs |= (grp != grp0);
+  // ---- stage 1 of the pipeline: index map + asynchronous gather of one item into buffer `buf` ----
+  auto prefetch = [&](long long item, int buf) -> bool {
+    uint8_t* base = smem + buf * buf_stride;
+    int* sSrc = reinterpret_cast<int*>(base + 3 * tile_bytes);
+    uint8_t* sGrp = reinterpret_cast<uint8_t*>(sSrc + npad);
+    const AttnItem it = decode_item(a, item);
+    int grp0 = 0;
+    win_source_token(g, it.win, 0, &grp0);
+    int differs = 0;
+    for (int t = tid; t < npad; t += kAttnThreads) {
+      int grp = kPadGroup;
+      int src = -2;  // rows in [ntok, npad): not part of the window at all
+      if (t < ntok) {
+        src = win_source_token(g, it.win, t, &grp);
+        differs |= (grp != grp0);
+      }
+      sSrc[t] = src;
+      sGrp[t] = static_cast<uint8_t>(grp);
     }
-    sSrc[t] = src;
-    sGrp[t] = static_cast<uint8_t>(grp);
-  }
-  // Most windows of a shifted block hold a single group: the mask is then all zeros and is skipped.
-  const bool masked = __syncthreads_or(differs) != 0 && g.shifted;
-  {
-    const uint32_t sq = smem_u32(sQ), sk = smem_u32(sK), sv = smem_u32(sV);
-    // 8 lanes move one 128-byte row of q, k and v each.
-    for (int idx = tid; idx < npad * 8; idx += kAttnThreads) {
+    // Most windows of a shifted block hold a single group: the mask is then all zeros and is skipped.
+    const bool masked = __syncthreads_or(differs) != 0 && g.shifted;
+    const long long row_base = static_cast<long long>(it.b) * a.tokens_per_batch;
+    const uint32_t sq = smem_u32(base), sk = sq + tile_bytes, sv = sk + tile_bytes;
+    for (int idx = tid; idx < npad * 8; idx += kAttnThreads) {  // 8 lanes move one 128-byte row of q, k, v
       const int t = idx >> 3;
       const int chunk = idx & 7;
       const int src = sSrc[t];
       const uint32_t off = swz(t, chunk);
       if (src >= 0) {
-        const __nv_bfloat16* p = a.qkv + (row_base + src) * ld + head * kHeadDim + chunk * 8;
+        const __nv_bfloat16* p = a.qkv + (row_base + src) * ld + it.head * kHeadDim + chunk * 8;
         cp_async_16(sq + off, p);
         cp_async_16(sk + off, p + a.dim);
         cp_async_16(sv + off, p + 2 * a.dim);
       } else if (src == -1) {
         // zero-padded token: x = 0, so q|k|v equal the projection bias (swin3d.py:476-482)
-        const __nv_bfloat16* p = a.pad_qkv + head * kHeadDim + chunk * 8;
+        const __nv_bfloat16* p = a.pad_qkv + it.head * kHeadDim + chunk * 8;
         cp_async_16(sq + off, p);
         cp_async_16(sk + off, p + a.dim);
         cp_async_16(sv + off, p + 2 * a.dim);
       } else {
         const uint4 z = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(sQ + off) = z;
-        *reinterpret_cast<uint4*>(sK + off) = z;
-        *reinterpret_cast<uint4*>(sV + off) = z;
+        *reinterpret_cast<uint4*>(base + off) = z;
+        *reinterpret_cast<uint4*>(base + tile_bytes + off) = z;
+        *reinterpret_cast<uint4*>(base + 2 * tile_bytes + off) = z;
       }
     }
-    cp_async_wait_all();
-  }
-  __syncthreads();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    return masked;
+  };
+
+  long long item = blockIdx.x;
+  if (item >= n_items) return;
+  bool masked_cur = prefetch(item, 0);
+  int buf = 0;
+  for (; item < n_items; item += gridDim.x, buf ^= 1) {
+    const long long next = item + gridDim.x;
+    bool masked_next = false;
+    if (next < n_items) {
+      masked_next = prefetch(next, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");  // this item's rows have landed; next stays in flight
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const bool masked = masked_cur;
+    uint8_t* sQ = smem + buf * buf_stride;
+    uint8_t* sK = sQ + tile_bytes;
+    uint8_t* sV = sK + tile_bytes;
+    const int* sSrc = reinterpret_cast<const int*>(sV + tile_bytes);
+    const uint8_t* sGrp = reinterpret_cast<const uint8_t*>(sSrc + npad);
+    const AttnItem it = decode_item(a, item);
+    const int head = it.head;
+    const long long row_base = static_cast<long long>(it.b) * a.tokens_per_batch;
 
   const int r0 = warp * 16;
   if (r0 < npad) {
@@ -294,6 +329,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) window_attention_kernel(const
       }
     }
   }
+    masked_cur = masked_next;
+    __syncthreads();  // every warp is done with this buffer before the prefetch two items ahead refills it
+  }
 }
 
 __global__ void window_index_dump_kernel(const WinGeom g, int* idx, uint8_t* grp) {
@@ -307,7 +345,8 @@ __global__ void window_index_dump_kernel(const WinGeom g, int* idx, uint8_t* grp
 
 static size_t attn_smem_bytes(int ntok) {
   const int npad = (ntok + 15) & ~15;
-  return static_cast<size_t>(npad) * kRowBytes * 3 + npad * sizeof(int) + npad + 16;
+  const size_t buf = static_cast<size_t>(npad) * kRowBytes * 3 + npad * sizeof(int) + npad;
+  return 2 * ((buf + 127) & ~static_cast<size_t>(127));  // two pipeline buffers
 }
 
 }  // namespace ab
@@ -394,8 +433,9 @@ extern "C" int ab_window_attention(const AbWindowAttention* p, void* stream) {
   }
   const long long items = static_cast<long long>(p->batch) * a.g.nwindows * p->num_heads;
   AB_CHECK_ARG(items < (1ll << 31), "ab_window_attention: too many work items");
-  window_attention_kernel<<<static_cast<unsigned>(items), kAttnThreads, smem,
-                            reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  const long long max_ctas = 2ll * sm_count();  // persistent: two CTAs per SM
+  const unsigned grid = static_cast<unsigned>(items < max_ctas ? items : max_ctas);
+  window_attention_kernel<<<grid, kAttnThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   AB_COUNT_LAUNCH(1);
   AB_CHECK_LAUNCH("ab_window_attention");
   return AB_OK;
