@@ -12,6 +12,8 @@
 // running concurrently share the same A rows in L2 while W stays L2-resident).
 //
 // Replaces: every nn.Linear on Aurora's forward path (see include/aurora_b200.h).
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -357,6 +359,235 @@ static int launch_gemm(const AbGemm* p, const GemmArgs& args, cudaStream_t strea
   return AB_OK;
 }
 
+
+// ================================================================================================
+// CTA-pair variant (cta_group::2): one 256 x 256 output tile per cluster of two CTAs.
+//
+// Each CTA stages its own 128 rows of A and HALF of the W tile (128 of the 256 N rows); the leader CTA
+// issues tcgen05.mma.cta_group::2 (M = 256) which reads both CTAs' shared memory and writes 128 accumulator
+// rows into each CTA's TMEM.  Per SM this cuts operand traffic per k-step from (128 + 256) to (128 + 128)
+// rows, i.e. shared-memory port load (tensor reads + TMA writes) from 192 to 128 B/clk — the single-CTA
+// kernel is capped at ~65 % tensor-pipe utilisation by that port (profiles/r01_*).
+//   full barrier   : leader's, count 2 (leader arrive.expect_tx for all four loads + peer remote arrive)
+//   empty barrier  : per CTA, signalled by a multicast tcgen05.commit from the leader
+//   tmem full      : per CTA, multicast commit;  tmem empty: leader's, 2 x 8 epilogue-warp arrivals
+// ================================================================================================
+template <bool kHalfIn>
+struct Gemm2Cfg {
+  static constexpr int BN = 256;                       // cluster tile N
+  static constexpr int kLoadN = 128;                   // W rows staged per CTA
+  static constexpr int kStageBytesA = kBlockM * kBlockK * 2;
+  static constexpr int kStageBytesB = kLoadN * kBlockK * 2;
+  static constexpr int kStageBytes = kStageBytesA + kStageBytesB;  // 32 KB
+  static constexpr int kStages = 6;
+  static constexpr uint32_t kTmemCols = 2 * BN;
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kStagingBytes = kNumEpiWarps * 4096;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024;
+};
+
+template <bool kHalfIn>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                     const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g) {
+  using Cfg = Gemm2Cfg<kHalfIn>;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  // Both CTAs must carve shared memory identically (descriptors / barrier offsets are shared).
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kStageBytesA;
+  uint8_t* smem_stage_out = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stage_out + Cfg::kStagingBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  cluster_sync_all();  // both CTAs resident before the pair-wide TMEM allocation
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_w);
+    if (g.tma_out) prefetch_tmap(&tmap_out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 2);   // used in the leader only
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 2 * kNumEpiWarps);  // used in the leader only
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before_sync();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_n = (g.n + BN - 1) / BN;
+  const int num_mp = (g.m + 2 * kBlockM - 1) / (2 * kBlockM);  // 256-row tile pairs
+  const int num_tiles = num_mp * num_n;
+  const int num_kb = (g.k + kBlockK - 1) / kBlockK;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs) =====
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile / num_n) * (2 * kBlockM) + rank * kBlockM;
+        const int n0 = (tile % num_n) * BN + rank * Cfg::kLoadN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          tma_load_2d_pair(smem_a + s * Cfg::kStageBytesA, &tmap_a, &full_bar[s], kb * kBlockK, m0);
+          tma_load_2d_pair(smem_b + s * Cfg::kStageBytesB, &tmap_w, &full_bar[s], kb * kBlockK, n0);
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);
+          else mbar_arrive_remote(&full_bar[s], 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ===== MMA issuer (leader CTA only) =====
+      constexpr uint32_t idesc = umma_idesc_f16kind_f32(2 * kBlockM, BN, kHalfIn);
+      uint32_t it = 0, tc = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tc) {
+        const uint32_t as = tc & 1u;
+        const uint32_t aph = (tc >> 1) & 1u;
+        mbar_wait(&tmem_empty_bar[as], aph ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem_a + s * Cfg::kStageBytesA);
+          const uint32_t b_addr = smem_u32(smem_b + s * Cfg::kStageBytesB);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t da = umma_desc_k_sw128(a_addr + k * kUmmaK * 2);
+            const uint64_t db = umma_desc_k_sw128(b_addr + k * kUmmaK * 2);
+            umma_bf16_ss_pair(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[s]);
+          if (kb == num_kb - 1) umma_commit_pair(&tmem_full_bar[as]);
+        }
+      }
+      // Let the last remote arrivals land on our barriers before the CTA may exit.
+      if (tc > 0) {
+        const uint32_t last = tc - 1;
+        mbar_wait(&tmem_empty_bar[last & 1u], (last >> 1) & 1u);
+        if (tc > 1) {
+          const uint32_t prev = tc - 2;
+          mbar_wait(&tmem_empty_bar[prev & 1u], (prev >> 1) & 1u);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (each CTA: its own 128 accumulator rows) =====
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    uint32_t tc = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tc) {
+      const int m0 = (tile / num_n) * (2 * kBlockM) + rank * kBlockM;
+      const int n0 = (tile % num_n) * BN;
+      const uint32_t as = tc & 1u;
+      const uint32_t aph = (tc >> 1) & 1u;
+      mbar_wait(&tmem_full_bar[as], aph);
+      tc_fence_after_sync();
+      const int row = m0 + q * 32 + lane;
+      if (g.tma_out) {
+        uint8_t* stage = smem_stage_out + (warp - 4) * 4096;
+        const uint32_t stage_row = smem_u32(stage) + lane * 128;
+#pragma unroll 1
+        for (int c = half * 64; c < BN; c += 128) {
+          if (n0 + c >= g.n) break;
+          uint32_t v0[32], v1[32];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c;
+          tmem_ld_32x32b_x32(taddr, v0);
+          tmem_ld_32x32b_x32(taddr + 32, v1);
+          tmem_ld_wait();
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+          epilogue_stage_half<BN>(g, v0, n0 + c, stage_row, lane, 0);
+          epilogue_stage_half<BN>(g, v1, n0 + c + 32, stage_row, lane, 4);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && m0 + q * 32 < g.m) {
+            tma_store_2d(&tmap_out, stage, n0 + c, m0 + q * 32);
+            tma_store_commit();
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c, v);
+          tmem_ld_wait();
+          epilogue_chunk<BN>(g, v, row, n0 + c);
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[as], 0);  // the leader's barrier collects both CTAs
+    }
+  }
+
+  if (warp >= 4 && g.tma_out && lane == 0) tma_store_wait_all<0>();
+  __syncwarp();
+  tc_fence_before_sync();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <bool kHalfIn>
+static int launch_gemm2(const AbGemm* p, const GemmArgs& args, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<kHalfIn>;
+  CUtensorMap ta, tw;
+  int rc = make_tmap_16bit_2d(&ta, p->a, p->m, p->k, p->lda, kBlockM, kBlockK, kHalfIn);
+  if (rc != AB_OK) return rc;
+  rc = make_tmap_16bit_2d(&tw, p->w, p->n, p->k, p->ldw, Cfg::kLoadN, kBlockK, kHalfIn);
+  if (rc != AB_OK) return rc;
+  CUtensorMap tout = ta;
+  if (args.tma_out) {
+    rc = make_tmap_16bit_2d(&tout, p->out_bf16, p->m, p->n, p->ld_bf16, 32, 64, args.out_half != 0);
+    if (rc != AB_OK) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_tn_kernel<kHalfIn>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("ab_gemm_bf16: cudaFuncSetAttribute(pair, smem=%d) failed: %s", Cfg::kSmemBytes,
+                cudaGetErrorString(e));
+      return AB_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const long long tiles = ceil_div_ll(p->m, 2 * kBlockM) * ceil_div_ll(p->n, Cfg::BN);
+  const long long max_clusters = sm_count() / 2;
+  const int clusters = static_cast<int>(tiles < max_clusters ? tiles : max_clusters);
+  gemm2_bf16_tn_kernel<kHalfIn><<<2 * clusters, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tw, tout, args);
+  AB_COUNT_LAUNCH(1);
+  AB_CHECK_LAUNCH("ab_gemm_bf16(pair)");
+  return AB_OK;
+}
+
 }  // namespace ab
 
 extern "C" int ab_gemm_bf16(const AbGemm* p, void* stream) {
@@ -398,6 +629,11 @@ extern "C" int ab_gemm_bf16(const AbGemm* p, void* stream) {
   a.tma_out = p->out_bf16 != nullptr && p->out_f32 == nullptr && p->residual == nullptr && al16(p->out_bf16) &&
               p->ld_bf16 % 8 == 0 && (p->bias == nullptr || (reinterpret_cast<uintptr_t>(p->bias) & 15u) == 0);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // Large problems run on CTA pairs (cta_group::2); small or narrow ones on the single-CTA kernel.
+  static const bool pair_disabled = getenv("AB_GEMM_NO_PAIR") != nullptr;
+  if (!pair_disabled && p->n >= 256 && p->m >= 1024) {
+    return p->in_dtype == AB_DT_F16 ? launch_gemm2<true>(p, a, s) : launch_gemm2<false>(p, a, s);
+  }
   if (p->in_dtype == AB_DT_F16) {
     if (p->n > 128) return launch_gemm<256, true>(p, a, s);
     if (p->n > 64) return launch_gemm<128, true>(p, a, s);

@@ -30,6 +30,11 @@ SHAPES = [
     (4096, 2048, 512),   # fc1 stage-1-like, many tiles per CTA
     (2048, 512, 2048),   # fc2-like, long K
     (5, 16, 8),          # minimum sizes
+    # CTA-pair (cta_group::2) kernel: M >= 1024 and N >= 256
+    (1300, 520, 192),    # M tail inside the second CTA of a pair, N tail, 3 k-blocks
+    (2049, 256, 72),     # one row into a new pair (second CTA fully out of bounds), K tail
+    (5000, 1536, 512),   # qkv-like, many tiles per cluster
+    (1024, 300, 64),     # N tail in the only N block
 ]
 
 
