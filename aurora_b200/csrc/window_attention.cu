@@ -14,6 +14,8 @@
 //   3. O += P V, normalise, stage through shared memory, 128-byte coalesced scatter to the source rows.
 //
 // Bound: HBM (reads 3D, writes D bf16 per token: arithmetic intensity ~72 FLOP/B).
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 #include "window_index.cuh"
@@ -334,6 +336,304 @@ __global__ void __launch_bounds__(kAttnThreads, 2) window_attention_kernel(const
   }
 }
 
+
+// ================================================================================================
+// tcgen05 / TMEM attention for FULL windows (2 x 6 x 12 = 144 tokens, head_dim 64): the production case.
+//
+// Persistent CTA per SM, warp-specialised, one (window, head) item per pipeline slot:
+//   warps 0-1 : loaders.  Warp w gathers the q/k/v rows of items n = w (mod 2) into smem stage w with cp.async
+//               (128-byte rows, hardware 128B-swizzle pattern: chunk ^= row & 7), computes the index map and
+//               group ids for that item (window_index.cuh), then makes the data visible to the async proxy.
+//   warp 2    : MMA issuer (one lane).  S = Q K^T as two M=128 x N=144 x K=64 tcgen05.mma tiles (rows 0-127 and
+//               32-159 of the Q tile; rows >= 144 are don't-care), accumulators in TMEM; later
+//               O = P V as two M=128 x N=64 x K=144 tiles with V as an MN-major B operand straight from the
+//               gathered [key][d] rows.  S(n+1) is issued before P V(n), so the tensor pipe works under the softmax.
+//   warps 3-7 : softmax + epilogue, ONE THREAD PER QUERY ROW (TMEM lane = row): tcgen05.ld the 144 logits, add
+//               the 0 / -100 shifted-window mask from one byte of group id per key, max / exp2 / sum without any
+//               shuffle, write P (bf16) into K-major swizzled smem, and — one item later — read O, scale by
+//               1 / sum and store the 128-byte output row at the source token (reverse + crop + un-roll).
+// TMEM columns: S tile 0 [0,144), O tile 0 [160,224), S tile 1 [256,400), O tile 1 [416,480).
+// ================================================================================================
+namespace tc {
+
+constexpr int kTok = 144;
+constexpr int kTileBytes = kTok * kRowBytes;       // 18 KB per q / k / v tile
+constexpr int kStageBytes = 3 * kTileBytes;        // 54 KB
+constexpr int kP0BlockBytes = 128 * kRowBytes;     // 16 KB: 128 rows x 64 keys
+constexpr int kP1BlockBytes = kP0BlockBytes;       // tile 1 (rows 32..159; only 128..143 are real) has the same shape
+constexpr int kOffP0 = 2 * kStageBytes;            // 108 KB
+constexpr int kOffP1 = kOffP0 + 3 * kP0BlockBytes; // 156 KB
+constexpr int kOffMeta = kOffP1 + 3 * kP1BlockBytes;  // 204 KB
+constexpr int kMetaBytes = 2048;
+constexpr int kSmemBytes = kOffMeta + kMetaBytes + 1024;
+constexpr int kThreads = 8 * 32;  // two warps per scheduler: every thread may use up to 255 registers
+constexpr int kTile1Row0 = 32;    // tile 1 covers Q rows 32..159, so rows 128..143 sit in TMEM lanes 96..111 (warp 3)
+constexpr uint32_t kColS0 = 0, kColO0 = 160, kColS1 = 256, kColO1 = 416;
+
+struct Meta {
+  int src[2][kTok];
+  uint8_t grp[2][kTok + 16];
+  int masked[2];
+  uint64_t full[2], empty[2], s_full, s_free, p_full, o_full, o_free;
+  uint32_t tmem_slot;
+};
+static_assert(sizeof(Meta) <= kMetaBytes, "meta area");
+
+__global__ void __launch_bounds__(kThreads, 1) window_attention_tc_kernel(const AttnArgs a) {
+  // warps: 0-1 loaders, 2 MMA issuer (+ barrier init, TMEM alloc), 3 softmax of rows 128..143 (TMEM lane
+  // quadrant 3 of tile 1), 4-7 softmax of rows 0..127 (quadrants 0..3 of tile 0).
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  Meta* meta = reinterpret_cast<Meta*>(smem + kOffMeta);
+  const WinGeom& g = a.g;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int ld = 3 * a.dim;
+  const long long n_items = static_cast<long long>(a.batch) * g.nwindows * a.num_heads;
+  const int cnt = static_cast<int>((n_items - blockIdx.x + gridDim.x - 1) / gridDim.x);  // items of this CTA
+
+  if (warp == 2 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&meta->full[i], 1);
+      mbar_init(&meta->empty[i], 1);
+    }
+    mbar_init(&meta->s_full, 1);
+    mbar_init(&meta->s_free, 5);
+    mbar_init(&meta->p_full, 5);
+    mbar_init(&meta->o_full, 1);
+    mbar_init(&meta->o_free, 5);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    __syncwarp();
+    tmem_alloc<512>(&meta->tmem_slot);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = meta->tmem_slot;
+
+  if (warp < 2) {
+    // ===== loaders =====
+    const int st = warp;
+    uint8_t* stage = smem + st * kStageBytes;
+    const uint32_t sq = smem_u32(stage), sk = sq + kTileBytes, sv = sk + kTileBytes;
+    for (int n = st; n < cnt; n += 2) {
+      mbar_wait(&meta->empty[st], (((n >> 1) & 1) ^ 1));
+      const AttnItem it = decode_item(a, blockIdx.x + static_cast<long long>(n) * gridDim.x);
+      int grp0 = 0;
+      win_source_token(g, it.win, 0, &grp0);
+      int differs = 0;
+      for (int t = lane; t < kTok; t += 32) {
+        int grp;
+        const int src = win_source_token(g, it.win, t, &grp);
+        differs |= (grp != grp0);
+        meta->src[st][t] = src;
+        meta->grp[st][t] = static_cast<uint8_t>(grp);
+      }
+      const int masked = (__any_sync(0xffffffffu, differs) && g.shifted) ? 1 : 0;
+      if (lane == 0) meta->masked[st] = masked;
+      __syncwarp();
+      const long long row_base = static_cast<long long>(it.b) * a.tokens_per_batch;
+      for (int idx = lane; idx < kTok * 8; idx += 32) {
+        const int t = idx >> 3, chunk = idx & 7;
+        const int src = meta->src[st][t];
+        const uint32_t off = swz(t, chunk);
+        const __nv_bfloat16* p = (src >= 0) ? a.qkv + (row_base + src) * ld + it.head * kHeadDim + chunk * 8
+                                            : a.pad_qkv + it.head * kHeadDim + chunk * 8;  // zero-padded token: bias
+        cp_async_16(sq + off, p);
+        cp_async_16(sk + off, p + a.dim);
+        cp_async_16(sv + off, p + 2 * a.dim);
+      }
+      cp_async_wait_all();
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&meta->full[st]);
+    }
+  } else if (warp == 2) {
+    if (lane == 0 && cnt > 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc_s = umma_idesc_f16kind_f32(128, kTok, false);
+      constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(128, kHeadDim);
+      auto issue_s = [&](int n) {
+        const uint32_t qa = smem_u32(smem + (n & 1) * kStageBytes);
+        const uint32_t ka = qa + kTileBytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t db = umma_desc_k_sw128(ka + k * 32);
+          umma_bf16_ss(tmem_base + kColS0, umma_desc_k_sw128(qa + k * 32), db, idesc_s, k != 0);
+          umma_bf16_ss(tmem_base + kColS1, umma_desc_k_sw128(qa + kTile1Row0 * kRowBytes + k * 32), db, idesc_s, k != 0);
+        }
+        umma_commit(&meta->s_full);
+      };
+      mbar_wait(&meta->full[0], 0);
+      tc_fence_after_sync();
+      issue_s(0);
+      for (int n = 0; n < cnt; ++n) {
+        if (n + 1 < cnt) {
+          mbar_wait(&meta->full[(n + 1) & 1], ((n + 1) >> 1) & 1);
+          mbar_wait(&meta->s_free, n & 1);  // the softmax warps have pulled S(n) out of TMEM
+          tc_fence_after_sync();
+          issue_s(n + 1);
+        }
+        mbar_wait(&meta->p_full, n & 1);
+        if (n > 0) mbar_wait(&meta->o_free, (n - 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t va = smem_u32(smem + (n & 1) * kStageBytes) + 2 * kTileBytes;
+        const uint32_t p0 = smem_u32(smem + kOffP0), p1 = smem_u32(smem + kOffP1);
+#pragma unroll
+        for (int j = 0; j < kTok / 16; ++j) {  // 9 k-steps of 16 keys
+          const uint64_t dv = umma_desc_k_sw128(va + j * 16 * kRowBytes);
+          umma_bf16_ss(tmem_base + kColO0, umma_desc_k_sw128(p0 + (j >> 2) * kP0BlockBytes + (j & 3) * 32), dv, idesc_o,
+                       j != 0);
+          umma_bf16_ss(tmem_base + kColO1, umma_desc_k_sw128(p1 + (j >> 2) * kP1BlockBytes + (j & 3) * 32), dv, idesc_o,
+                       j != 0);
+        }
+        umma_commit(&meta->o_full);
+        umma_commit(&meta->empty[n & 1]);  // q / k / v of this stage are consumed
+      }
+    }
+  } else {
+    // ===== softmax + epilogue (warps 3..7): thread = query row =====
+    const int tile = (warp == 3) ? 1 : 0;
+    const int lrow = (warp & 3) * 32 + lane;           // row inside the tile (TMEM lane)
+    const int row = tile * kTile1Row0 + lrow;          // window token
+    const bool valid = row < kTok;
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_addr + (tile ? kColS1 : kColS0);
+    const uint32_t o_addr = tmem_base + lane_addr + (tile ? kColO1 : kColO0);
+    uint8_t* p_base = smem + (tile ? kOffP1 : kOffP0);
+    const int p_block = tile ? kP1BlockBytes : kP0BlockBytes;
+    constexpr float kC = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) in the exp2 domain
+
+    int prev_src = -1;
+    float prev_inv = 0.f;
+    long long prev_item = 0;
+    auto epilogue = [&](int n_prev) {
+      mbar_wait(&meta->o_full, n_prev & 1);
+      tc_fence_after_sync();
+      uint32_t o0[32], o1[32];
+      tmem_ld_32x32b_x32(o_addr, o0);
+      tmem_ld_32x32b_x32(o_addr + 32, o1);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&meta->o_free);
+      if (valid && prev_src >= 0) {
+        const AttnItem it = decode_item(a, prev_item);
+        uint4* dst = reinterpret_cast<uint4*>(a.out + (static_cast<long long>(it.b) * a.tokens_per_batch + prev_src) * a.dim +
+                                              it.head * kHeadDim);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o0[8 * c + 0]) * prev_inv, __uint_as_float(o0[8 * c + 1]) * prev_inv);
+          u.y = pack_bf16x2(__uint_as_float(o0[8 * c + 2]) * prev_inv, __uint_as_float(o0[8 * c + 3]) * prev_inv);
+          u.z = pack_bf16x2(__uint_as_float(o0[8 * c + 4]) * prev_inv, __uint_as_float(o0[8 * c + 5]) * prev_inv);
+          u.w = pack_bf16x2(__uint_as_float(o0[8 * c + 6]) * prev_inv, __uint_as_float(o0[8 * c + 7]) * prev_inv);
+          dst[c] = u;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o1[8 * c + 0]) * prev_inv, __uint_as_float(o1[8 * c + 1]) * prev_inv);
+          u.y = pack_bf16x2(__uint_as_float(o1[8 * c + 2]) * prev_inv, __uint_as_float(o1[8 * c + 3]) * prev_inv);
+          u.z = pack_bf16x2(__uint_as_float(o1[8 * c + 4]) * prev_inv, __uint_as_float(o1[8 * c + 5]) * prev_inv);
+          u.w = pack_bf16x2(__uint_as_float(o1[8 * c + 6]) * prev_inv, __uint_as_float(o1[8 * c + 7]) * prev_inv);
+          dst[4 + c] = u;
+        }
+      }
+    };
+
+    for (int n = 0; n < cnt; ++n) {
+      const int st = n & 1;
+      mbar_wait(&meta->full[st], (n >> 1) & 1);  // index map / group ids of this item are in smem
+      const int my_src = valid ? meta->src[st][row] : -1;
+      const int my_grp = valid ? meta->grp[st][row] : 0;
+      const int masked = meta->masked[st];
+      mbar_wait(&meta->s_full, n & 1);
+      tc_fence_after_sync();
+      float sv[kTok];
+      {
+        uint32_t t0[32], t1[32], t2[32], t3[32], t4[16];
+        tmem_ld_32x32b_x32(s_addr, t0);
+        tmem_ld_32x32b_x32(s_addr + 32, t1);
+        tmem_ld_32x32b_x32(s_addr + 64, t2);
+        tmem_ld_32x32b_x32(s_addr + 96, t3);
+        tmem_ld_32x32b_x16(s_addr + 128, t4);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          sv[j] = __uint_as_float(t0[j]);
+          sv[32 + j] = __uint_as_float(t1[j]);
+          sv[64 + j] = __uint_as_float(t2[j]);
+          sv[96 + j] = __uint_as_float(t3[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sv[128 + j] = __uint_as_float(t4[j]);
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&meta->s_free);  // S(n) is in registers: the next S may overwrite TMEM
+      if (masked) {
+        // 0 / -100 on the scaled logits == 0 / -800 on the raw q.k products (scale 1/8)
+        const uint32_t* g4 = reinterpret_cast<const uint32_t*>(meta->grp[st]);
+#pragma unroll
+        for (int w4 = 0; w4 < kTok / 4; ++w4) {
+          const uint32_t gw = g4[w4];  // broadcast load: four keys' group ids
+          if (static_cast<int>(gw & 0xff) != my_grp) sv[4 * w4] -= 800.f;
+          if (static_cast<int>((gw >> 8) & 0xff) != my_grp) sv[4 * w4 + 1] -= 800.f;
+          if (static_cast<int>((gw >> 16) & 0xff) != my_grp) sv[4 * w4 + 2] -= 800.f;
+          if (static_cast<int>(gw >> 24) != my_grp) sv[4 * w4 + 3] -= 800.f;
+        }
+      }
+      float mx = sv[0];
+#pragma unroll
+      for (int j = 1; j < kTok; ++j) mx = fmaxf(mx, sv[j]);
+      const float nm = -mx * kC;
+      float sum = 0.f;
+      uint32_t pk[kTok / 2];
+#pragma unroll
+      for (int j = 0; j < kTok / 2; ++j) {
+        const float e0 = ex2_approx(fmaf(sv[2 * j], kC, nm));
+        const float e1 = ex2_approx(fmaf(sv[2 * j + 1], kC, nm));
+        sum += e0 + e1;
+        pk[j] = pack_bf16x2(e0, e1);
+      }
+      // P(n) may only replace P(n-1) once P V(n-1) has retired; that is what o_full(n-1) says.  Doing the
+      // previous item's epilogue here keeps the tensor pipe busy with P V(n-1) / S(n+1) under this softmax.
+      if (n > 0) epilogue(n - 1);
+      {
+        const uint32_t prow = smem_u32(p_base) + lrow * kRowBytes;
+#pragma unroll
+        for (int ch = 0; ch < kTok / 8; ++ch) {
+          const uint32_t addr = prow + (ch >> 3) * p_block + (((ch & 7) ^ (lrow & 7)) << 4);
+          if (valid)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * ch]), "r"(pk[4 * ch + 1]),
+                         "r"(pk[4 * ch + 2]), "r"(pk[4 * ch + 3])
+                         : "memory");
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&meta->p_full);
+      prev_src = my_src;
+      prev_inv = 1.f / sum;
+      prev_item = blockIdx.x + static_cast<long long>(n) * gridDim.x;
+    }
+    if (cnt > 0) epilogue(cnt - 1);
+  }
+
+  __syncwarp();
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace tc
+
 __global__ void window_index_dump_kernel(const WinGeom g, int* idx, uint8_t* grp) {
   const int total = g.nwindows * g.ntok;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -420,6 +720,27 @@ extern "C" int ab_window_attention(const AbWindowAttention* p, void* stream) {
   a.num_heads = p->num_heads;
   a.dim = p->num_heads * kHeadDim;
   a.tokens_per_batch = static_cast<long long>(p->res[0]) * p->res[1] * p->res[2];
+  // Full 144-token windows (every production resolution) run on the tcgen05 / TMEM kernel.
+  static const bool tc_disabled = getenv("AB_ATTN_NO_TC") != nullptr;
+  if (!tc_disabled && a.g.ntok == tc::kTok && a.bias == nullptr) {
+    static bool tc_attr_set = false;
+    if (!tc_attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(tc::window_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           tc::kSmemBytes);
+      if (e != cudaSuccess) {
+        set_error("ab_window_attention: cudaFuncSetAttribute(tc) failed: %s", cudaGetErrorString(e));
+        return AB_ERR_CUDA;
+      }
+      tc_attr_set = true;
+    }
+    const long long tc_items = static_cast<long long>(p->batch) * a.g.nwindows * p->num_heads;
+    const unsigned tc_grid = static_cast<unsigned>(tc_items < sm_count() ? tc_items : sm_count());
+    // pad_qkv may be NULL when the grid has no padding: the loader then never dereferences it
+    tc::window_attention_tc_kernel<<<tc_grid, tc::kThreads, tc::kSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    AB_COUNT_LAUNCH(1);
+    AB_CHECK_LAUNCH("ab_window_attention(tc)");
+    return AB_OK;
+  }
   const size_t smem = attn_smem_bytes(a.g.ntok);
   static bool attr_set = false;
   if (!attr_set) {
