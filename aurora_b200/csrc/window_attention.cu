@@ -15,6 +15,7 @@
 //
 // Bound: HBM (reads 3D, writes D bf16 per token: arithmetic intensity ~72 FLOP/B).
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -37,6 +38,7 @@ struct AttnArgs {
   WinGeom g;
   int batch, num_heads, dim;
   long long tokens_per_batch;
+  int box_rows;  // tc kernel: consecutive window-row tokens moved by one TMA box (0 = cp.async gather)
 };
 
 __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc) {
@@ -379,7 +381,8 @@ struct Meta {
 };
 static_assert(sizeof(Meta) <= kMetaBytes, "meta area");
 
-__global__ void __launch_bounds__(kThreads, 1) window_attention_tc_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(kThreads, 1)
+window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs a) {
   // warps: 0-1 loaders, 2 MMA issuer (+ barrier init, TMEM alloc), 3 softmax of rows 128..143 (TMEM lane
   // quadrant 3 of tile 1), 4-7 softmax of rows 0..127 (quadrants 0..3 of tile 0).
   extern __shared__ uint8_t smem_raw[];
@@ -392,6 +395,7 @@ __global__ void __launch_bounds__(kThreads, 1) window_attention_tc_kernel(const 
   const long long n_items = static_cast<long long>(a.batch) * g.nwindows * a.num_heads;
   const int cnt = static_cast<int>((n_items - blockIdx.x + gridDim.x - 1) / gridDim.x);  // items of this CTA
 
+  if (warp == 0 && lane == 0 && a.box_rows > 0) prefetch_tmap(&tmap_qkv);
   if (warp == 2 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&meta->full[i], 1);
@@ -435,6 +439,45 @@ __global__ void __launch_bounds__(kThreads, 1) window_attention_tc_kernel(const 
       if (lane == 0) meta->masked[st] = masked;
       __syncwarp();
       const long long row_base = static_cast<long long>(it.b) * a.tokens_per_batch;
+      if (a.box_rows > 0) {
+        // TMA gather: every run of `box_rows` consecutive in-window tokens along W is either all padding or one
+        // contiguous piece of the token stream (the host picked box_rows as the gcd of all run boundaries), so
+        // it is ONE 2-D box {64 columns, box_rows rows} of the [tokens, 3D] qkv matrix per q / k / v.  The
+        // 128B swizzle is applied by the TMA unit, completion is counted on the stage's mbarrier.
+        const int r = a.box_rows;
+        const int groups_per_row = g.ws[2] / r;
+        const int units = g.ws[0] * g.ws[1] * groups_per_row;  // (ic, ih, group)
+        uint32_t bytes = 0;
+        for (int u = lane; u < units; u += 32) {
+          const int t0 = (u / groups_per_row) * g.ws[2] + (u % groups_per_row) * r;  // first window token of the run
+          const int src = meta->src[st][t0];
+          const uint32_t off = static_cast<uint32_t>(t0) * kRowBytes;
+          if (src >= 0) {
+            const int grow = static_cast<int>(row_base + src);
+            const int col = it.head * kHeadDim;
+            tma_load_2d(stage + off, &tmap_qkv, &meta->full[st], col, grow);
+            tma_load_2d(stage + kTileBytes + off, &tmap_qkv, &meta->full[st], col + a.dim, grow);
+            tma_load_2d(stage + 2 * kTileBytes + off, &tmap_qkv, &meta->full[st], col + 2 * a.dim, grow);
+            bytes += 3u * r * kRowBytes;
+          } else {
+            // zero-padded tokens: x = 0, so q | k | v are the projection bias
+            for (int i = 0; i < r * 8; ++i) {
+              const int t = t0 + (i >> 3), chunk = i & 7;
+              const uint4* pb = reinterpret_cast<const uint4*>(a.pad_qkv + it.head * kHeadDim + chunk * 8);
+              const uint32_t o2 = swz(t, chunk);
+              *reinterpret_cast<uint4*>(stage + o2) = __ldg(pb);
+              *reinterpret_cast<uint4*>(stage + kTileBytes + o2) = __ldg(pb + a.dim / 8);
+              *reinterpret_cast<uint4*>(stage + 2 * kTileBytes + o2) = __ldg(pb + 2 * a.dim / 8);
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+        fence_proxy_async_smem();  // bias fills (generic proxy) -> tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive_expect_tx(&meta->full[st], bytes);
+        continue;
+      }
       for (int idx = lane; idx < kTok * 8; idx += 32) {
         const int t = idx >> 3, chunk = idx & 7;
         const int src = meta->src[st][t];
@@ -706,6 +749,7 @@ extern "C" int ab_window_attention(const AbWindowAttention* p, void* stream) {
     AB_CHECK_ARG(p->res[a] > 0 && p->window[a] > 0 && p->shift[a] >= 0 && p->shift[a] < p->window[a],
                  "ab_window_attention: bad res/window/shift on axis %d", a);
   AttnArgs a;
+  a.box_rows = 0;
   a.g = make_win_geom(p->res, p->window, p->shift, p->warped);
   AB_CHECK_ARG(a.g.ntok <= kMaxTok, "ab_window_attention: window of %d tokens exceeds the supported %d", a.g.ntok,
                kMaxTok);
@@ -733,10 +777,32 @@ extern "C" int ab_window_attention(const AbWindowAttention* p, void* stream) {
       }
       tc_attr_set = true;
     }
+    // Largest run length R such that every run of R in-window tokens along W is all-padding or contiguous.
+    static const bool tma_disabled = getenv("AB_ATTN_NO_TMA") != nullptr;
+    a.box_rows = 0;
+    CUtensorMap tq;
+    memset(&tq, 0, sizeof(tq));
+    if (!tma_disabled) {
+      auto gcd = [](int x, int y) { while (y) { int t = x % y; x = y; y = t; } return x; };
+      int r = a.g.ws[2];
+      for (int kw = 0; kw < a.g.nwin[2]; ++kw) {
+        int prev_valid = -1, prev_src = 0;
+        for (int i = 0; i < a.g.ws[2]; ++i) {
+          const int q = kw * a.g.ws[2] + i - a.g.lo[2];
+          const int valid = q >= 0 && q < a.g.res[2];
+          const int src = valid ? (q + a.g.ss[2]) % a.g.res[2] : -1;
+          if (i > 0 && (valid != prev_valid || (valid && src != prev_src + 1))) r = gcd(r, i);
+          prev_valid = valid;
+          prev_src = src;
+        }
+      }
+      const long long rows = static_cast<long long>(p->batch) * a.tokens_per_batch;
+      if (make_tmap_16bit_2d(&tq, p->qkv, rows, 3ll * a.dim, 3ll * a.dim, r, kHeadDim, false) == AB_OK) a.box_rows = r;
+    }
     const long long tc_items = static_cast<long long>(p->batch) * a.g.nwindows * p->num_heads;
     const unsigned tc_grid = static_cast<unsigned>(tc_items < sm_count() ? tc_items : sm_count());
     // pad_qkv may be NULL when the grid has no padding: the loader then never dereferences it
-    tc::window_attention_tc_kernel<<<tc_grid, tc::kThreads, tc::kSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    tc::window_attention_tc_kernel<<<tc_grid, tc::kThreads, tc::kSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(tq, a);
     AB_COUNT_LAUNCH(1);
     AB_CHECK_LAUNCH("ab_window_attention(tc)");
     return AB_OK;
