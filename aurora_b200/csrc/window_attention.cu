@@ -372,6 +372,37 @@ constexpr int kThreads = 8 * 32;  // two warps per scheduler: every thread may u
 constexpr int kTile1Row0 = 32;    // tile 1 covers Q rows 32..159, so rows 128..143 sit in TMEM lanes 96..111 (warp 3)
 constexpr uint32_t kColS0 = 0, kColO0 = 160, kColS1 = 256, kColO1 = 416;
 
+// win_source_token() for the fixed (2, 6, 12) window with the window already decoded to (k0, k1, k2):
+// compile-time divisors only (the generic routine's runtime divisions made the single loader warp the
+// bottleneck of the whole pipeline).
+__device__ __forceinline__ int tc_source_token(const WinGeom& g, int k0, int k1, int k2, int tok, int* group) {
+  const int i[3] = {tok / 72, (tok / 12) % 6, tok % 12};
+  const int k[3] = {k0, k1, k2};
+  constexpr int kWs[3] = {2, 6, 12};
+  int src[3];
+  int grp = 0;
+  bool valid = true;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int q = k[a] * kWs[a] + i[a] - g.lo[a];
+    valid = valid && (q >= 0) && (q < g.res[a]);
+    int sft = q + g.ss[a];
+    if (sft >= g.res[a]) sft -= g.res[a];
+    src[a] = sft;
+    int b;
+    if (g.ss[a] == 0) b = 2;
+    else b = (q < g.res[a] - kWs[a]) ? 0 : ((q < g.res[a] - g.ss[a]) ? 1 : 2);
+    if (a == 2 && g.warped && b == 1) b = 2;
+    grp = grp * 3 + b;
+  }
+  if (!valid) {
+    *group = kPadGroup;
+    return -1;
+  }
+  *group = grp;
+  return (src[0] * g.res[1] + src[1]) * g.res[2] + src[2];
+}
+
 struct Meta {
   int src[2][kTok];
   uint8_t grp[2][kTok + 16];
@@ -425,12 +456,15 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const A
     for (int n = st; n < cnt; n += 2) {
       mbar_wait(&meta->empty[st], (((n >> 1) & 1) ^ 1));
       const AttnItem it = decode_item(a, blockIdx.x + static_cast<long long>(n) * gridDim.x);
+      const int k2 = it.win % g.nwin[2];
+      const int k1 = (it.win / g.nwin[2]) % g.nwin[1];
+      const int k0 = it.win / (g.nwin[2] * g.nwin[1]);
       int grp0 = 0;
-      win_source_token(g, it.win, 0, &grp0);
+      tc_source_token(g, k0, k1, k2, 0, &grp0);
       int differs = 0;
       for (int t = lane; t < kTok; t += 32) {
         int grp;
-        const int src = win_source_token(g, it.win, t, &grp);
+        const int src = tc_source_token(g, k0, k1, k2, t, &grp);
         differs |= (grp != grp0);
         meta->src[st][t] = src;
         meta->grp[st][t] = static_cast<uint8_t>(grp);
@@ -629,19 +663,21 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const A
           if (static_cast<int>(gw >> 24) != my_grp) sv[4 * w4 + 3] -= 800.f;
         }
       }
-      float mx = sv[0];
+      float mxa[4] = {sv[0], sv[1], sv[2], sv[3]};  // four independent chains: one warp per scheduler has no TLP
 #pragma unroll
-      for (int j = 1; j < kTok; ++j) mx = fmaxf(mx, sv[j]);
+      for (int j = 4; j < kTok; ++j) mxa[j & 3] = fmaxf(mxa[j & 3], sv[j]);
+      const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
       const float nm = -mx * kC;
-      float sum = 0.f;
+      float suma[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t pk[kTok / 2];
 #pragma unroll
       for (int j = 0; j < kTok / 2; ++j) {
         const float e0 = ex2_approx(fmaf(sv[2 * j], kC, nm));
         const float e1 = ex2_approx(fmaf(sv[2 * j + 1], kC, nm));
-        sum += e0 + e1;
+        suma[j & 3] += e0 + e1;
         pk[j] = pack_bf16x2(e0, e1);
       }
+      const float sum = (suma[0] + suma[1]) + (suma[2] + suma[3]);
       // P(n) may only replace P(n-1) once P V(n-1) has retired; that is what o_full(n-1) says.  Doing the
       // previous item's epilogue here keeps the tensor pipe busy with P V(n-1) / S(n+1) under this softmax.
       if (n > 0) epilogue(n - 1);
