@@ -362,11 +362,15 @@ constexpr int kTok = 144;
 constexpr int kTileBytes = kTok * kRowBytes;       // 18 KB per q / k / v tile
 constexpr int kStageBytes = 3 * kTileBytes;        // 54 KB
 constexpr int kP0BlockBytes = 128 * kRowBytes;     // 16 KB: 128 rows x 64 keys
-constexpr int kP1BlockBytes = kP0BlockBytes;       // tile 1 (rows 32..159; only 128..143 are real) has the same shape
-constexpr int kOffP0 = 2 * kStageBytes;            // 108 KB
-constexpr int kOffP1 = kOffP0 + 3 * kP0BlockBytes; // 156 KB
-constexpr int kOffMeta = kOffP1 + 3 * kP1BlockBytes;  // 204 KB
-constexpr int kMetaBytes = 2048;
+constexpr int kStages = 3;                         // q/k/v ring: a stage is only released by P V, loads must run ahead
+constexpr int kP1BlockBytes = 16 * kRowBytes;      // tile 1: only rows 128..143 (TMEM lanes 96..111) are real -> 2 KB
+constexpr int kOffP0 = kStages * kStageBytes;      // 162 KB
+constexpr int kOffP1 = kOffP0 + 3 * kP0BlockBytes; // 210 KB: three 2 KB blocks holding tile-1 rows 96..111
+constexpr int kOffMeta = kOffP1 + 3 * kP1BlockBytes;  // 216 KB
+constexpr int kMetaBytes = 2560;
+// The tile-1 A operand of P V starts 96 rows BEFORE its live rows (inside the P0 area): the M=128 MMA reads 128
+// rows, rows 0..95 / 112..127 are don't-care (their accumulator rows are never read) but must be mapped memory.
+constexpr int kP1Rewind = 96 * kRowBytes;
 constexpr int kSmemBytes = kOffMeta + kMetaBytes + 1024;
 constexpr int kThreads = 8 * 32;  // two warps per scheduler: every thread may use up to 255 registers
 constexpr int kTile1Row0 = 32;    // tile 1 covers Q rows 32..159, so rows 128..143 sit in TMEM lanes 96..111 (warp 3)
@@ -404,10 +408,11 @@ __device__ __forceinline__ int tc_source_token(const WinGeom& g, int k0, int k1,
 }
 
 struct Meta {
-  int src[2][kTok];
-  uint8_t grp[2][kTok + 16];
-  int masked[2];
-  uint64_t full[2], empty[2], s_full, s_free, p_full, o_full, o_free;
+  int src[kStages][kTok];
+  uint8_t grp[kStages][kTok + 16];
+  int masked[kStages];
+  int pad_;
+  uint64_t full[kStages], empty[kStages], s_full, s_free, p_full, o_full, o_free;
   uint32_t tmem_slot;
 };
 static_assert(sizeof(Meta) <= kMetaBytes, "meta area");
@@ -428,7 +433,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const A
 
   if (warp == 0 && lane == 0 && a.box_rows > 0) prefetch_tmap(&tmap_qkv);
   if (warp == 2 && lane == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(&meta->full[i], 1);
       mbar_init(&meta->empty[i], 1);
     }
@@ -449,12 +454,12 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const A
   const uint32_t tmem_base = meta->tmem_slot;
 
   if (warp < 2) {
-    // ===== loaders =====
-    const int st = warp;
-    uint8_t* stage = smem + st * kStageBytes;
-    const uint32_t sq = smem_u32(stage), sk = sq + kTileBytes, sv = sk + kTileBytes;
-    for (int n = st; n < cnt; n += 2) {
-      mbar_wait(&meta->empty[st], (((n >> 1) & 1) ^ 1));
+    // ===== loaders: warp w takes items n = w (mod 2); item n lives in ring stage n % kStages =====
+    for (int n = warp; n < cnt; n += 2) {
+      const int st = n % kStages;
+      uint8_t* stage = smem + st * kStageBytes;
+      const uint32_t sq = smem_u32(stage), sk = sq + kTileBytes, sv = sk + kTileBytes;
+      mbar_wait(&meta->empty[st], ((((n / kStages) & 1)) ^ 1));
       const AttnItem it = decode_item(a, blockIdx.x + static_cast<long long>(n) * gridDim.x);
       const int k2 = it.win % g.nwin[2];
       const int k1 = (it.win / g.nwin[2]) % g.nwin[1];
@@ -533,7 +538,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const A
       constexpr uint32_t idesc_s = umma_idesc_f16kind_f32(128, kTok, false);
       constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(128, kHeadDim);
       auto issue_s = [&](int n) {
-        const uint32_t qa = smem_u32(smem + (n & 1) * kStageBytes);
+        const uint32_t qa = smem_u32(smem + (n % kStages) * kStageBytes);
         const uint32_t ka = qa + kTileBytes;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -548,7 +553,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const A
       issue_s(0);
       for (int n = 0; n < cnt; ++n) {
         if (n + 1 < cnt) {
-          mbar_wait(&meta->full[(n + 1) & 1], ((n + 1) >> 1) & 1);
+          mbar_wait(&meta->full[(n + 1) % kStages], ((n + 1) / kStages) & 1);
           mbar_wait(&meta->s_free, n & 1);  // the softmax warps have pulled S(n) out of TMEM
           tc_fence_after_sync();
           issue_s(n + 1);
@@ -556,8 +561,8 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const A
         mbar_wait(&meta->p_full, n & 1);
         if (n > 0) mbar_wait(&meta->o_free, (n - 1) & 1);
         tc_fence_after_sync();
-        const uint32_t va = smem_u32(smem + (n & 1) * kStageBytes) + 2 * kTileBytes;
-        const uint32_t p0 = smem_u32(smem + kOffP0), p1 = smem_u32(smem + kOffP1);
+        const uint32_t va = smem_u32(smem + (n % kStages) * kStageBytes) + 2 * kTileBytes;
+        const uint32_t p0 = smem_u32(smem + kOffP0), p1 = smem_u32(smem + kOffP1) - kP1Rewind;
 #pragma unroll
         for (int j = 0; j < kTok / 16; ++j) {  // 9 k-steps of 16 keys
           const uint64_t dv = umma_desc_k_sw128(va + j * 16 * kRowBytes);
@@ -567,7 +572,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const A
                        j != 0);
         }
         umma_commit(&meta->o_full);
-        umma_commit(&meta->empty[n & 1]);  // q / k / v of this stage are consumed
+        umma_commit(&meta->empty[n % kStages]);  // q / k / v of this stage are consumed
       }
     }
   } else {
@@ -579,8 +584,10 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const A
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t s_addr = tmem_base + lane_addr + (tile ? kColS1 : kColS0);
     const uint32_t o_addr = tmem_base + lane_addr + (tile ? kColO1 : kColO0);
+    // P rows in smem: tile 0 row = lrow; tile 1 keeps only its 16 live rows (lane = lrow - 96)
     uint8_t* p_base = smem + (tile ? kOffP1 : kOffP0);
     const int p_block = tile ? kP1BlockBytes : kP0BlockBytes;
+    const int p_row = tile ? (lrow - 96) : lrow;
     constexpr float kC = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) in the exp2 domain
 
     int prev_src = -1;
@@ -622,8 +629,8 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const A
     };
 
     for (int n = 0; n < cnt; ++n) {
-      const int st = n & 1;
-      mbar_wait(&meta->full[st], (n >> 1) & 1);  // index map / group ids of this item are in smem
+      const int st = n % kStages;
+      mbar_wait(&meta->full[st], (n / kStages) & 1);  // index map / group ids of this item are in smem
       const int my_src = valid ? meta->src[st][row] : -1;
       const int my_grp = valid ? meta->grp[st][row] : 0;
       const int masked = meta->masked[st];
@@ -682,7 +689,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const A
       // previous item's epilogue here keeps the tensor pipe busy with P V(n-1) / S(n+1) under this softmax.
       if (n > 0) epilogue(n - 1);
       {
-        const uint32_t prow = smem_u32(p_base) + lrow * kRowBytes;
+        const uint32_t prow = smem_u32(p_base) + p_row * kRowBytes;
 #pragma unroll
         for (int ch = 0; ch < kTok / 8; ++ch) {
           const uint32_t addr = prow + (ch >> 3) * p_block + (((ch & 7) ^ (lrow & 7)) << 4);
