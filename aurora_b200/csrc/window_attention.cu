@@ -409,7 +409,7 @@ __device__ __forceinline__ int tc_source_token(const WinGeom& g, int k0, int k1,
 
 struct Meta {
   int src[kStages][kTok];
-  uint8_t grp[kStages][kTok + 16];
+  alignas(16) uint8_t grp[kStages][kTok + 16];
   int masked[kStages];
   int pad_;
   uint64_t full[kStages], empty[kStages], s_full, s_free, p_full, o_full, o_free;
@@ -498,10 +498,13 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const A
             tma_load_2d(stage + kTileBytes + off, &tmap_qkv, &meta->full[st], col + a.dim, grow);
             tma_load_2d(stage + 2 * kTileBytes + off, &tmap_qkv, &meta->full[st], col + 2 * a.dim, grow);
             bytes += 3u * r * kRowBytes;
-          } else {
-            // zero-padded tokens: x = 0, so q | k | v are the projection bias
-            for (int i = 0; i < r * 8; ++i) {
-              const int t = t0 + (i >> 3), chunk = i & 7;
+          }
+        }
+        if (g.nwindows * kTok != g.res[0] * g.res[1] * g.res[2]) {
+          // zero-padded tokens (x = 0): q | k | v are the projection bias; filled by the whole warp, 16 B per lane
+          for (int idx = lane; idx < kTok * 8; idx += 32) {
+            const int t = idx >> 3, chunk = idx & 7;
+            if (meta->src[st][t] < 0) {
               const uint4* pb = reinterpret_cast<const uint4*>(a.pad_qkv + it.head * kHeadDim + chunk * 8);
               const uint32_t o2 = swz(t, chunk);
               *reinterpret_cast<uint4*>(stage + o2) = __ldg(pb);
@@ -660,14 +663,21 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const A
       if (lane == 0) mbar_arrive(&meta->s_free);  // S(n) is in registers: the next S may overwrite TMEM
       if (masked) {
         // 0 / -100 on the scaled logits == 0 / -800 on the raw q.k products (scale 1/8)
-        const uint32_t* g4 = reinterpret_cast<const uint32_t*>(meta->grp[st]);
+        const uint4* g16 = reinterpret_cast<const uint4*>(meta->grp[st]);
+        const uint32_t mine = static_cast<uint32_t>(my_grp) * 0x01010101u;
 #pragma unroll
-        for (int w4 = 0; w4 < kTok / 4; ++w4) {
-          const uint32_t gw = g4[w4];  // broadcast load: four keys' group ids
-          if (static_cast<int>(gw & 0xff) != my_grp) sv[4 * w4] -= 800.f;
-          if (static_cast<int>((gw >> 8) & 0xff) != my_grp) sv[4 * w4 + 1] -= 800.f;
-          if (static_cast<int>((gw >> 16) & 0xff) != my_grp) sv[4 * w4 + 2] -= 800.f;
-          if (static_cast<int>(gw >> 24) != my_grp) sv[4 * w4 + 3] -= 800.f;
+        for (int w16 = 0; w16 < kTok / 16; ++w16) {
+          const uint4 gv = g16[w16];  // broadcast load: sixteen keys' group ids
+          const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+          for (int w4 = 0; w4 < 4; ++w4) {
+            const uint32_t ne = __vcmpne4(gw[w4], mine);  // 0xff per key of another group
+            const int j = 16 * w16 + 4 * w4;
+            if (ne & 0x000000ffu) sv[j] -= 800.f;
+            if (ne & 0x0000ff00u) sv[j + 1] -= 800.f;
+            if (ne & 0x00ff0000u) sv[j + 2] -= 800.f;
+            if (ne & 0xff000000u) sv[j + 3] -= 800.f;
+          }
         }
       }
       float mxa[4] = {sv[0], sv[1], sv[2], sv[3]};  // four independent chains: one warp per scheduler has no TLP
