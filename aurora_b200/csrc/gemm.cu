@@ -379,17 +379,15 @@ struct Gemm2Cfg {
   static constexpr int kStageBytesA = kBlockM * kBlockK * 2;
   static constexpr int kStageBytesB = kLoadN * kBlockK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;  // 32 KB
-  static constexpr int kStages = 5;
+  static constexpr int kStages = 6;
   static constexpr uint32_t kTmemCols = 2 * BN;
   static constexpr int kBarrierBytes = 256;
-  static constexpr int kEpiWarps = 16;  // four per TMEM lane quadrant: one 64-column store box each per tile
-  static constexpr int kThreads = 128 + kEpiWarps * 32;
-  static constexpr int kStagingBytes = kEpiWarps * 4096;
+  static constexpr int kStagingBytes = kNumEpiWarps * 4096;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024;
 };
 
 template <bool kHalfIn>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg<kHalfIn>::kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                      const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g) {
   using Cfg = Gemm2Cfg<kHalfIn>;
@@ -424,7 +422,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 2 * Cfg::kEpiWarps);  // used in the leader only
+      mbar_init(&tmem_empty_bar[s], 2 * kNumEpiWarps);  // used in the leader only
     }
     fence_mbar_init();
   }
@@ -498,9 +496,9 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue (each CTA: its own 128 accumulator rows; warp = (lane quadrant, 64-column box)) =====
+    // ===== epilogue (each CTA: its own 128 accumulator rows) =====
     const int q = warp & 3;
-    const int box = (warp - 4) >> 2;  // 0..3
+    const int half = (warp - 4) >> 2;
     uint32_t tc = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tc) {
       const int m0 = (tile / num_n) * (2 * kBlockM) + rank * kBlockM;
@@ -510,17 +508,18 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       mbar_wait(&tmem_full_bar[as], aph);
       tc_fence_after_sync();
       const int row = m0 + q * 32 + lane;
-      const int c = box * 64;
       if (g.tma_out) {
         uint8_t* stage = smem_stage_out + (warp - 4) * 4096;
         const uint32_t stage_row = smem_u32(stage) + lane * 128;
-        if (n0 + c < g.n) {  // warp-uniform
+#pragma unroll 1
+        for (int c = half * 64; c < BN; c += 128) {
+          if (n0 + c >= g.n) break;
           uint32_t v0[32], v1[32];
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c;
           tmem_ld_32x32b_x32(taddr, v0);
           tmem_ld_32x32b_x32(taddr + 32, v1);
           tmem_ld_wait();
-          if (lane == 0) tma_store_wait_read<0>();  // this warp's previous box has left the staging buffer
+          if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
           epilogue_stage_half<BN>(g, v0, n0 + c, stage_row, lane, 0);
           epilogue_stage_half<BN>(g, v1, n0 + c + 32, stage_row, lane, 4);
@@ -533,11 +532,11 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         }
       } else {
 #pragma unroll 1
-        for (int cc = c; cc < c + 64; cc += 32) {
+        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
           uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + cc, v);
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c, v);
           tmem_ld_wait();
-          epilogue_chunk<BN>(g, v, row, n0 + cc);
+          epilogue_chunk<BN>(g, v, row, n0 + c);
         }
       }
       tc_fence_before_sync();
@@ -583,7 +582,7 @@ static int launch_gemm2(const AbGemm* p, const GemmArgs& args, cudaStream_t stre
   const long long tiles = ceil_div_ll(p->m, 2 * kBlockM) * ceil_div_ll(p->n, Cfg::BN);
   const long long max_clusters = sm_count() / 2;
   const int clusters = static_cast<int>(tiles < max_clusters ? tiles : max_clusters);
-  gemm2_bf16_tn_kernel<kHalfIn><<<2 * clusters, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tw, tout, args);
+  gemm2_bf16_tn_kernel<kHalfIn><<<2 * clusters, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tw, tout, args);
   AB_COUNT_LAUNCH(1);
   AB_CHECK_LAUNCH("ab_gemm_bf16(pair)");
   return AB_OK;
