@@ -103,6 +103,91 @@ __global__ void __launch_bounds__(256) perceiver_attention_kernel(const PercArgs
   }
 }
 
+// Few keys, many queries (decoder: 13 level queries x 3 latent keys): one warp per LOCATION keeps the K / V rows
+// of all (<= 4) keys in registers and loops over the queries, so every K / V row is read from memory once
+// instead of once per query.
+template <int E, int kHalf>
+__global__ void __launch_bounds__(256) perceiver_attention_fewkeys_kernel(const PercArgs a) {
+  constexpr int kMaxK = 4;
+  // dim / E lanes (one or two warps) share a location; `lane` is the position inside that group
+  const int lanes_per_loc = a.dim / E;
+  const long long gl = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long loc = gl / lanes_per_loc;
+  const int lane = static_cast<int>(gl % lanes_per_loc);
+  if (loc >= a.nloc) return;
+  const int lanes_per_head = a.dh / E;  // <= 32 and aligned, so a head never straddles a warp
+  uint32_t kp[kMaxK][E / 2], vp[kMaxK][E / 2];  // packed 16-bit pairs
+#pragma unroll
+  for (int c = 0; c < kMaxK; ++c) {
+    if (c < a.lk) {
+      const uint16_t* krow = a.kv + (static_cast<long long>(c) * a.nloc + loc) * a.ld_kv + lane * E;
+#pragma unroll
+      for (int i = 0; i < E / 8; ++i) {
+        const uint4 ku = __ldg(reinterpret_cast<const uint4*>(krow) + i);
+        const uint4 vu = __ldg(reinterpret_cast<const uint4*>(krow + a.dim) + i);
+        kp[c][4 * i] = ku.x; kp[c][4 * i + 1] = ku.y; kp[c][4 * i + 2] = ku.z; kp[c][4 * i + 3] = ku.w;
+        vp[c][4 * i] = vu.x; vp[c][4 * i + 1] = vu.y; vp[c][4 * i + 2] = vu.z; vp[c][4 * i + 3] = vu.w;
+      }
+    }
+  }
+  for (int iq = 0; iq < a.lq; ++iq) {
+    const float* qp = a.q + static_cast<long long>(iq) * a.dim + lane * E;
+    float q[E];
+#pragma unroll
+    for (int i = 0; i < E; i += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(qp + i));
+      q[i] = v.x * a.scale;
+      q[i + 1] = v.y * a.scale;
+      q[i + 2] = v.z * a.scale;
+      q[i + 3] = v.w * a.scale;
+    }
+    float sc[kMaxK];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < kMaxK; ++c) {
+      sc[c] = -INFINITY;
+      if (c < a.lk) {
+        float d = 0.f;
+#pragma unroll
+        for (int i = 0; i < E / 2; ++i) {
+          const float2 kk = unpack16x2<kHalf>(kp[c][i]);
+          d = fmaf(q[2 * i], kk.x, d);
+          d = fmaf(q[2 * i + 1], kk.y, d);
+        }
+        for (int o = 1; o < lanes_per_head; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        sc[c] = d;
+        mx = fmaxf(mx, d);
+      }
+    }
+    float l = 0.f;
+    float acc[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxK; ++c) {
+      if (c < a.lk) {
+        const float p = __expf(sc[c] - mx);
+        l += p;
+#pragma unroll
+        for (int i = 0; i < E / 2; ++i) {
+          const float2 vv = unpack16x2<kHalf>(vp[c][i]);
+          acc[2 * i] = fmaf(p, vv.x, acc[2 * i]);
+          acc[2 * i + 1] = fmaf(p, vv.y, acc[2 * i + 1]);
+        }
+      }
+    }
+    const float inv = 1.f / l;
+    uint16_t* orow = a.out + (static_cast<long long>(iq) * a.nloc + loc) * a.ld_out + lane * E;
+#pragma unroll
+    for (int i = 0; i < E / 8; ++i) {
+      float t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = acc[8 * i + j] * inv;
+      reinterpret_cast<uint4*>(orow)[i] = pack16x8<kHalf>(t);
+    }
+  }
+}
+
 // y[r, n] = act(sum_k x[r, k] W[n, k] + b[n]) ; one warp per output element, lanes stride over K.
 // act_in: apply SiLU to x on load (nn.Sequential(SiLU, Linear)); act_out: SiLU on the result.
 __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
@@ -162,6 +247,24 @@ extern "C" int ab_perceiver_attention(const float* q, const void* kv_bf16, void*
                    ((head_dim / e) & (head_dim / e - 1)) == 0,
                "ab_perceiver_attention: unsupported width (dim=%d head_dim=%d): need dim/32 in {4,8,16,32} dividing "
                "head_dim by a power of two", dim, head_dim);
+  if (lk <= 4 && lq > lk && dim % 256 == 0) {
+    // decoder shape: keep the few K / V rows in registers; dim / E lanes per location
+    const int e_fk = dim % 512 == 0 ? 16 : 8;
+    const unsigned grid_fk = static_cast<unsigned>(ceil_div_ll(nloc * (dim / e_fk), 256));
+    cudaStream_t sfk = reinterpret_cast<cudaStream_t>(stream);
+    const bool hfk = dtype == AB_DT_F16;
+#define AB_PERC_FK(EE)                                                                 \
+  do {                                                                                 \
+    if (hfk) perceiver_attention_fewkeys_kernel<EE, 1><<<grid_fk, 256, 0, sfk>>>(a);   \
+    else perceiver_attention_fewkeys_kernel<EE, 0><<<grid_fk, 256, 0, sfk>>>(a);       \
+  } while (0)
+    if (e_fk == 8) AB_PERC_FK(8);
+    else AB_PERC_FK(16);
+#undef AB_PERC_FK
+    AB_COUNT_LAUNCH(1);
+    AB_CHECK_LAUNCH("ab_perceiver_attention");
+    return AB_OK;
+  }
   const long long total = nloc * lq;  // warps
   const unsigned grid = static_cast<unsigned>(ceil_div_ll(total * 32, 256));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

@@ -283,18 +283,15 @@ def main() -> None:
     import aurora_b200 as ab
     from aurora_b200 import cabi
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    distributed = world > 1
+    from aurora_b200 import dist as abd
+    import torch.distributed as dist
+
+    rank, world, local_rank = abd.env_world()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if distributed:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=dev)
+    distributed = abd.init_process_group("nccl", dev)
 
     cls, h, w, levels = WORKLOADS[args.workload]
     model = getattr(ab, cls)(_init="empty").to(dev).eval()
@@ -391,9 +388,8 @@ def main() -> None:
 
     # ---- max over ranks ----
     if distributed:
-        t = torch.tensor([ms, e2e_ms or 0.0], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = float(t[0]), (float(t[1]) if e2e_ms is not None else None)
+        mx = abd.max_over_ranks([ms, e2e_ms or 0.0], device=dev)
+        ms, e2e_ms = mx[0], (mx[1] if e2e_ms is not None else None)
 
     if rank == 0:
         cpu = None
