@@ -48,11 +48,13 @@ WORKLOADS = {
     "aurora-small-0.25deg-721x1440x13L": ("AuroraSmallPretrained", 721, 1440, LEVELS13),
     "aurora-small-17x32x4L": ("AuroraSmallPretrained", 17, 32, (100, 250, 500, 850)),
     "aurora-highres-0.1deg-1801x3600x13L": ("AuroraHighRes", 1801, 3600, LEVELS13),
+    "aurora-airpollution-0.4deg-451x900x13L": ("AuroraAirPollution", 451, 900, LEVELS13),
 }
 DEFAULT_WORKLOAD = "aurora-0.25deg-721x1440x13L"
 
 # Algorithmic work of one forward step, 2 flops per MAC.
 ALGO_TFLOP = {"aurora-0.25deg-721x1440x13L": 96.8, "aurora-highres-0.1deg-1801x3600x13L": 91.7,
+              "aurora-airpollution-0.4deg-451x900x13L": 69.2,
               "aurora-small-0.25deg-721x1440x13L": 12.6, "aurora-small-17x32x4L": 0.004}
 
 
@@ -266,7 +268,7 @@ def run_reference_arm(args) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
