@@ -210,6 +210,11 @@ class AbWindowAttention(C.Structure):
         ("num_heads", C.c_int32),
         ("head_dim", C.c_int32),
         ("warped", C.c_int32),
+        ("slab_h_begin", C.c_int32),
+        ("slab_h_rows", C.c_int32),
+        ("slab_halo", C.c_int32),
+        ("reserved_", C.c_int32),
+        ("halo_qkv", C.c_void_p),
     ]
 
 
@@ -305,10 +310,13 @@ def window_index_map_host(res, window, shift, warped: bool = True):
 
 def window_attention(qkv: torch.Tensor, out: torch.Tensor, *, batch: int, res, window, shift, num_heads: int,
                      pad_qkv: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
-                     warped: bool = True) -> None:
+                     warped: bool = True, slab: Optional[tuple[int, int]] = None,
+                     halo_qkv: Optional[torch.Tensor] = None) -> None:
+    """`slab=(h_begin, h_rows)`: qkv / out hold only those rows of the global grid `res` (latitude sharding);
+    `halo_qkv` is bf16 [2, C, halo, W, 3D] with the rows above / below the slab (cyclic)."""
     assert qkv.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and qkv.is_contiguous() and out.is_contiguous()
     d = num_heads * 64
-    tokens = batch * res[0] * res[1] * res[2]
+    tokens = batch * res[0] * res[1] * res[2] if slab is None else res[0] * slab[1] * res[2]
     assert qkv.shape == (tokens, 3 * d) and out.shape == (tokens, d), (qkv.shape, out.shape, tokens, d)
     a = AbWindowAttention()
     a.qkv, a.out = ptr(qkv), ptr(out)
@@ -321,6 +329,14 @@ def window_attention(qkv: torch.Tensor, out: torch.Tensor, *, batch: int, res, w
     a.batch = batch
     a.res, a.window, a.shift = _i3(res), _i3(window), _i3(shift)
     a.num_heads, a.head_dim, a.warped = num_heads, 64, int(warped)
+    if slab is not None:
+        a.slab_h_begin, a.slab_h_rows = int(slab[0]), int(slab[1])
+        if halo_qkv is not None:
+            assert halo_qkv.dtype == torch.bfloat16 and halo_qkv.is_contiguous() and halo_qkv.dim() == 5
+            assert halo_qkv.shape[0] == 2 and halo_qkv.shape[1] == res[0] and halo_qkv.shape[3] == res[2]
+            assert halo_qkv.shape[4] == 3 * d
+            a.slab_halo = halo_qkv.shape[2]
+            a.halo_qkv = ptr(halo_qkv)
     nw, nt, _ = window_geometry(res, window, shift)
     with _Timed("window_attention", work=4.0 * batch * nw * num_heads * nt * nt * 64, nbytes=8.0 * tokens * d):
         check(lib().ab_window_attention(C.byref(a), _s()), "ab_window_attention")

@@ -39,6 +39,10 @@ struct AttnArgs {
   int batch, num_heads, dim;
   long long tokens_per_batch;
   int box_rows;  // tc kernel: consecutive window-row tokens moved by one TMA box (0 = cp.async gather)
+  // Latitude slab (multi-GPU sharding of one forecast): qkv / out hold only rows [h_begin, h_begin + h_rows) of the
+  // global (C, H, W) grid; `halo` rows above and below (cyclic in H) come from halo_qkv [2][C][halo][W][3D].
+  int slab, h_begin, h_rows, halo, kh_begin, kh_count;
+  const __nv_bfloat16* halo_qkv;
 };
 
 __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc) {
@@ -367,7 +371,7 @@ constexpr int kP1BlockBytes = 16 * kRowBytes;      // tile 1: only rows 128..143
 constexpr int kOffP0 = kStages * kStageBytes;      // 162 KB
 constexpr int kOffP1 = kOffP0 + 3 * kP0BlockBytes; // 210 KB: three 2 KB blocks holding tile-1 rows 96..111
 constexpr int kOffMeta = kOffP1 + 3 * kP1BlockBytes;  // 216 KB
-constexpr int kMetaBytes = 2560;
+constexpr int kMetaBytes = 4352;
 // The tile-1 A operand of P V starts 96 rows BEFORE its live rows (inside the P0 area): the M=128 MMA reads 128
 // rows, rows 0..95 / 112..127 are don't-care (their accumulator rows are never read) but must be mapped memory.
 constexpr int kP1Rewind = 96 * kRowBytes;
@@ -407,7 +411,69 @@ __device__ __forceinline__ int tc_source_token(const WinGeom& g, int k0, int k1,
   return (src[0] * g.res[1] + src[1]) * g.res[2] + src[2];
 }
 
+// Window of pipeline item `item` as (head, k0, k1, k2); with a latitude slab only the `kh_count` window rows that
+// touch the slab are enumerated (cyclically from kh_begin).
+struct TcItem {
+  int head, k0, k1, k2, b;
+};
+__device__ __forceinline__ TcItem tc_decode(const AttnArgs& a, long long item) {
+  TcItem it;
+  it.head = static_cast<int>(item % a.num_heads);
+  item /= a.num_heads;
+  const WinGeom& g = a.g;
+  if (a.slab) {
+    it.k2 = static_cast<int>(item % g.nwin[2]);
+    item /= g.nwin[2];
+    it.k1 = (a.kh_begin + static_cast<int>(item % a.kh_count)) % g.nwin[1];
+    it.k0 = static_cast<int>(item / a.kh_count);
+    it.b = 0;
+  } else {
+    const int win = static_cast<int>(item % g.nwindows);
+    it.b = static_cast<int>(item / g.nwindows);
+    it.k2 = win % g.nwin[2];
+    it.k1 = (win / g.nwin[2]) % g.nwin[1];
+    it.k0 = win / (g.nwin[2] * g.nwin[1]);
+  }
+  return it;
+}
+
+constexpr int kHaloFlag = 1 << 30;
+
+// Global source token -> (row to LOAD from, row to STORE to).  Whole grid: both are the token itself.  Slab: own
+// rows live in the local buffer, halo rows in the halo buffer (load only: their outputs belong to a neighbour).
+__device__ __forceinline__ void tc_translate(const AttnArgs& a, int src, int* load_row, int* store_row) {
+  if (src < 0 || !a.slab) {
+    *load_row = src;
+    *store_row = src;
+    return;
+  }
+  const WinGeom& g = a.g;
+  const int w = src % g.res[2];
+  const int t = src / g.res[2];
+  const int h = t % g.res[1];
+  const int c = t / g.res[1];
+  int dh = h - a.h_begin;
+  if (dh < 0) dh += g.res[1];
+  if (dh < a.h_rows) {
+    *load_row = (c * a.h_rows + dh) * g.res[2] + w;
+    *store_row = *load_row;
+    return;
+  }
+  *store_row = -1;
+  int dt = h - (a.h_begin - a.halo);
+  dt %= g.res[1];
+  if (dt < 0) dt += g.res[1];
+  if (dt < a.halo) {
+    *load_row = kHaloFlag | ((c * a.halo + dt) * g.res[2] + w);
+    return;
+  }
+  int db = (h - (a.h_begin + a.h_rows)) % g.res[1];
+  if (db < 0) db += g.res[1];
+  *load_row = kHaloFlag | (((g.res[0] + c) * a.halo + db) * g.res[2] + w);  // host guarantees db < halo
+}
+
 struct Meta {
+  int lsrc[kStages][kTok];  // row to load from (kHaloFlag: halo buffer), -1 = zero padding
   int src[kStages][kTok];
   alignas(16) uint8_t grp[kStages][kTok + 16];
   int masked[kStages];
@@ -418,7 +484,8 @@ struct Meta {
 static_assert(sizeof(Meta) <= kMetaBytes, "meta area");
 
 __global__ void __launch_bounds__(kThreads, 1)
-window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs a) {
+window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_halo,
+                           const AttnArgs a) {
   // warps: 0-1 loaders, 2 MMA issuer (+ barrier init, TMEM alloc), 3 softmax of rows 128..143 (TMEM lane
   // quadrant 3 of tile 1), 4-7 softmax of rows 0..127 (quadrants 0..3 of tile 0).
   extern __shared__ uint8_t smem_raw[];
@@ -428,7 +495,9 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const A
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int ld = 3 * a.dim;
-  const long long n_items = static_cast<long long>(a.batch) * g.nwindows * a.num_heads;
+  const long long n_windows = a.slab ? static_cast<long long>(g.nwin[0]) * a.kh_count * g.nwin[2]
+                                     : static_cast<long long>(a.batch) * g.nwindows;
+  const long long n_items = n_windows * a.num_heads;
   const int cnt = static_cast<int>((n_items - blockIdx.x + gridDim.x - 1) / gridDim.x);  // items of this CTA
 
   if (warp == 0 && lane == 0 && a.box_rows > 0) prefetch_tmap(&tmap_qkv);
@@ -460,18 +529,17 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const A
       uint8_t* stage = smem + st * kStageBytes;
       const uint32_t sq = smem_u32(stage), sk = sq + kTileBytes, sv = sk + kTileBytes;
       mbar_wait(&meta->empty[st], ((((n / kStages) & 1)) ^ 1));
-      const AttnItem it = decode_item(a, blockIdx.x + static_cast<long long>(n) * gridDim.x);
-      const int k2 = it.win % g.nwin[2];
-      const int k1 = (it.win / g.nwin[2]) % g.nwin[1];
-      const int k0 = it.win / (g.nwin[2] * g.nwin[1]);
+      const TcItem it = tc_decode(a, blockIdx.x + static_cast<long long>(n) * gridDim.x);
       int grp0 = 0;
-      tc_source_token(g, k0, k1, k2, 0, &grp0);
+      tc_source_token(g, it.k0, it.k1, it.k2, 0, &grp0);
       int differs = 0;
       for (int t = lane; t < kTok; t += 32) {
-        int grp;
-        const int src = tc_source_token(g, k0, k1, k2, t, &grp);
+        int grp, lrow, srow;
+        const int src = tc_source_token(g, it.k0, it.k1, it.k2, t, &grp);
+        tc_translate(a, src, &lrow, &srow);
         differs |= (grp != grp0);
-        meta->src[st][t] = src;
+        meta->lsrc[st][t] = lrow;
+        meta->src[st][t] = srow;
         meta->grp[st][t] = static_cast<uint8_t>(grp);
       }
       const int masked = (__any_sync(0xffffffffu, differs) && g.shifted) ? 1 : 0;
@@ -489,14 +557,16 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const A
         uint32_t bytes = 0;
         for (int u = lane; u < units; u += 32) {
           const int t0 = (u / groups_per_row) * g.ws[2] + (u % groups_per_row) * r;  // first window token of the run
-          const int src = meta->src[st][t0];
+          const int src = meta->lsrc[st][t0];
           const uint32_t off = static_cast<uint32_t>(t0) * kRowBytes;
           if (src >= 0) {
-            const int grow = static_cast<int>(row_base + src);
+            const bool from_halo = (src & kHaloFlag) != 0;
+            const int grow = from_halo ? (src & ~kHaloFlag) : static_cast<int>(row_base + src);
+            const CUtensorMap* tm = from_halo ? &tmap_halo : &tmap_qkv;
             const int col = it.head * kHeadDim;
-            tma_load_2d(stage + off, &tmap_qkv, &meta->full[st], col, grow);
-            tma_load_2d(stage + kTileBytes + off, &tmap_qkv, &meta->full[st], col + a.dim, grow);
-            tma_load_2d(stage + 2 * kTileBytes + off, &tmap_qkv, &meta->full[st], col + 2 * a.dim, grow);
+            tma_load_2d(stage + off, tm, &meta->full[st], col, grow);
+            tma_load_2d(stage + kTileBytes + off, tm, &meta->full[st], col + a.dim, grow);
+            tma_load_2d(stage + 2 * kTileBytes + off, tm, &meta->full[st], col + 2 * a.dim, grow);
             bytes += 3u * r * kRowBytes;
           }
         }
@@ -504,7 +574,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const A
           // zero-padded tokens (x = 0): q | k | v are the projection bias; filled by the whole warp, 16 B per lane
           for (int idx = lane; idx < kTok * 8; idx += 32) {
             const int t = idx >> 3, chunk = idx & 7;
-            if (meta->src[st][t] < 0) {
+            if (meta->lsrc[st][t] < 0) {
               const uint4* pb = reinterpret_cast<const uint4*>(a.pad_qkv + it.head * kHeadDim + chunk * 8);
               const uint32_t o2 = swz(t, chunk);
               *reinterpret_cast<uint4*>(stage + o2) = __ldg(pb);
@@ -522,10 +592,12 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const A
       }
       for (int idx = lane; idx < kTok * 8; idx += 32) {
         const int t = idx >> 3, chunk = idx & 7;
-        const int src = meta->src[st][t];
+        const int src = meta->lsrc[st][t];
         const uint32_t off = swz(t, chunk);
-        const __nv_bfloat16* p = (src >= 0) ? a.qkv + (row_base + src) * ld + it.head * kHeadDim + chunk * 8
-                                            : a.pad_qkv + it.head * kHeadDim + chunk * 8;  // zero-padded token: bias
+        const __nv_bfloat16* p;
+        if (src < 0) p = a.pad_qkv + it.head * kHeadDim + chunk * 8;  // zero-padded token: bias
+        else if (src & kHaloFlag) p = a.halo_qkv + static_cast<long long>(src & ~kHaloFlag) * ld + it.head * kHeadDim + chunk * 8;
+        else p = a.qkv + (row_base + src) * ld + it.head * kHeadDim + chunk * 8;
         cp_async_16(sq + off, p);
         cp_async_16(sk + off, p + a.dim);
         cp_async_16(sv + off, p + 2 * a.dim);
@@ -607,7 +679,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const A
       __syncwarp();
       if (lane == 0) mbar_arrive(&meta->o_free);
       if (valid && prev_src >= 0) {
-        const AttnItem it = decode_item(a, prev_item);
+        const TcItem it = tc_decode(a, prev_item);
         uint4* dst = reinterpret_cast<uint4*>(a.out + (static_cast<long long>(it.b) * a.tokens_per_batch + prev_src) * a.dim +
                                               it.head * kHeadDim);
 #pragma unroll
@@ -809,6 +881,51 @@ extern "C" int ab_window_attention(const AbWindowAttention* p, void* stream) {
   const bool has_pad = a.g.nwindows * a.g.ntok != p->res[0] * p->res[1] * p->res[2];
   AB_CHECK_ARG(!has_pad || p->pad_qkv != nullptr,
                "ab_window_attention: the window grid is zero-padded; pad_qkv (bf16 projection bias) is required");
+  a.slab = p->slab_h_rows > 0 ? 1 : 0;
+  a.h_begin = p->slab_h_begin;
+  a.h_rows = p->slab_h_rows;
+  a.halo = p->slab_halo;
+  a.kh_begin = 0;
+  a.kh_count = a.g.nwin[1];
+  a.halo_qkv = reinterpret_cast<const __nv_bfloat16*>(p->halo_qkv);
+  if (a.slab) {
+    AB_CHECK_ARG(p->batch == 1, "ab_window_attention: a latitude slab needs batch == 1");
+    AB_CHECK_ARG(a.g.ntok == tc::kTok && p->bias == nullptr,
+                 "ab_window_attention: latitude slabs are supported for full 144-token windows only");
+    AB_CHECK_ARG(a.h_begin >= 0 && a.h_begin < p->res[1] && a.h_rows <= p->res[1],
+                 "ab_window_attention: bad slab rows [%d, +%d) of %d", a.h_begin, a.h_rows, p->res[1]);
+    AB_CHECK_ARG(a.h_rows == p->res[1] || (a.halo >= a.g.ws[1] - 1 && p->halo_qkv != nullptr),
+                 "ab_window_attention: a slab needs halo_qkv with at least %d halo rows", a.g.ws[1] - 1);
+    // window rows (cyclic range) that contain at least one owned source row
+    const int nk = a.g.nwin[1], hh = p->res[1];
+    int first = -1, count = 0;
+    bool any_gap = false;
+    auto touches = [&](int kh) {
+      for (int i = 0; i < a.g.ws[1]; ++i) {
+        const int q = kh * a.g.ws[1] + i - a.g.lo[1];
+        if (q < 0 || q >= hh) continue;
+        int d = (q + a.g.ss[1]) % hh - a.h_begin;
+        if (d < 0) d += hh;
+        if (d < a.h_rows) return true;
+      }
+      return false;
+    };
+    for (int kh = 0; kh < nk; ++kh) {
+      if (touches(kh)) ++count;
+      else any_gap = true;
+    }
+    if (!any_gap) {
+      first = 0;
+    } else {
+      for (int kh = 0; kh < nk; ++kh)
+        if (touches(kh) && !touches((kh + nk - 1) % nk)) first = kh;
+    }
+    AB_CHECK_ARG(first >= 0 && count > 0, "ab_window_attention: the slab touches no window row");
+    for (int j = 0; j < count; ++j)
+      AB_CHECK_ARG(touches((first + j) % nk), "ab_window_attention: window rows of the slab are not contiguous");
+    a.kh_begin = first;
+    a.kh_count = count;
+  }
   a.qkv = reinterpret_cast<const __nv_bfloat16*>(p->qkv);
   a.pad_qkv = reinterpret_cast<const __nv_bfloat16*>(p->pad_qkv);
   a.out = reinterpret_cast<__nv_bfloat16*>(p->out);
@@ -833,8 +950,9 @@ extern "C" int ab_window_attention(const AbWindowAttention* p, void* stream) {
     // Largest run length R such that every run of R in-window tokens along W is all-padding or contiguous.
     static const bool tma_disabled = getenv("AB_ATTN_NO_TMA") != nullptr;
     a.box_rows = 0;
-    CUtensorMap tq;
+    CUtensorMap tq, th;
     memset(&tq, 0, sizeof(tq));
+    memset(&th, 0, sizeof(th));
     if (!tma_disabled) {
       auto gcd = [](int x, int y) { while (y) { int t = x % y; x = y; y = t; } return x; };
       int r = a.g.ws[2];
@@ -849,16 +967,28 @@ extern "C" int ab_window_attention(const AbWindowAttention* p, void* stream) {
           prev_src = src;
         }
       }
-      const long long rows = static_cast<long long>(p->batch) * a.tokens_per_batch;
+      const long long rows = a.slab ? static_cast<long long>(p->res[0]) * a.h_rows * p->res[2]
+                                    : static_cast<long long>(p->batch) * a.tokens_per_batch;
       if (make_tmap_16bit_2d(&tq, p->qkv, rows, 3ll * a.dim, 3ll * a.dim, r, kHeadDim, false) == AB_OK) a.box_rows = r;
+      if (a.box_rows > 0 && a.slab && a.halo > 0 && a.halo_qkv != nullptr) {
+        const long long hrows = 2ll * p->res[0] * a.halo * p->res[2];
+        if (make_tmap_16bit_2d(&th, p->halo_qkv, hrows, 3ll * a.dim, 3ll * a.dim, r, kHeadDim, false) != AB_OK)
+          a.box_rows = 0;
+      }
     }
-    const long long tc_items = static_cast<long long>(p->batch) * a.g.nwindows * p->num_heads;
+    const long long tc_windows = a.slab ? static_cast<long long>(a.g.nwin[0]) * a.kh_count * a.g.nwin[2]
+                                        : static_cast<long long>(p->batch) * a.g.nwindows;
+    const long long tc_items = tc_windows * p->num_heads;
     const unsigned tc_grid = static_cast<unsigned>(tc_items < sm_count() ? tc_items : sm_count());
     // pad_qkv may be NULL when the grid has no padding: the loader then never dereferences it
-    tc::window_attention_tc_kernel<<<tc_grid, tc::kThreads, tc::kSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(tq, a);
+    tc::window_attention_tc_kernel<<<tc_grid, tc::kThreads, tc::kSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(tq, th, a);
     AB_COUNT_LAUNCH(1);
     AB_CHECK_LAUNCH("ab_window_attention(tc)");
     return AB_OK;
+  }
+  if (a.slab) {
+    set_error("ab_window_attention: latitude slabs need the tcgen05 kernel (AB_ATTN_NO_TC is set?)");
+    return AB_ERR_UNSUPPORTED;
   }
   const size_t smem = attn_smem_bytes(a.g.ntok);
   static bool attr_set = false;

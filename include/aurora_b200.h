@@ -110,6 +110,15 @@ typedef struct AbWindowAttention {
   int32_t num_heads;
   int32_t head_dim;    /* must be 64 */
   int32_t warped;
+  /* Latitude slab (one forecast sharded over GPUs along H; all zero = whole grid).  qkv / out then hold only the
+   * token rows [slab_h_begin, slab_h_begin + slab_h_rows) of the GLOBAL (C, H, W) grid, level-major
+   * [C, slab_h_rows, W, .], batch must be 1; `halo_qkv` bf16 [2, C, slab_halo, W, 3*D] holds the slab_halo rows
+   * above ([0]: rows h_begin-halo .. h_begin-1) and below ([1]: rows h_end .. h_end+halo-1) the slab, cyclic in H
+   * (received from the neighbouring ranks).  Every window touching the slab is computed, only the slab's own
+   * rows are written.  slab_halo >= window[1] - 1 is required; full 144-token windows only. */
+  int32_t slab_h_begin, slab_h_rows, slab_halo;
+  int32_t reserved_;
+  const void* halo_qkv;
 } AbWindowAttention;
 
 int ab_window_attention(const AbWindowAttention* p, void* stream);

@@ -309,3 +309,45 @@ def test_unpatchify_matches_reference_layout(p, h, w):
     torch.testing.assert_close(outs[0][:h], ref0, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(outs[1][:h], ref1, rtol=1e-5, atol=1e-5)
     assert torch.isnan(outs[0][h]).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# latitude slabs (multi-GPU sharding of one forecast), emulated on one GPU
+# ------------------------------------------------------------------------------------------------
+def _slab_views(full_qkv, res, d3, h0, rows, halo):
+    c, h, w = res
+    g = full_qkv.view(c, h, w, d3)
+    idx_own = [(h0 + i) % h for i in range(rows)]
+    idx_top = [(h0 - halo + i) % h for i in range(halo)]
+    idx_bot = [(h0 + rows + i) % h for i in range(halo)]
+    local = g[:, idx_own].contiguous().view(c * rows * w, d3)
+    halo_t = torch.stack((g[:, idx_top], g[:, idx_bot]), 0).contiguous()  # [2, C, halo, W, 3D]
+    return local, halo_t, idx_own
+
+
+@pytest.mark.parametrize("res,heads,splits", [((4, 24, 24), 2, (0, 12, 24)), ((4, 45, 90), 2, (0, 12, 24, 36, 45)),
+                                              ((4, 36, 48), 4, (0, 8, 20, 36))])
+@pytest.mark.parametrize("shifted", [False, True])
+def test_window_attention_latitude_slabs_equal_whole_grid(res, heads, splits, shifted):
+    """Every rank's slab result must equal the corresponding rows of the whole-grid result bit for bit."""
+    from aurora_b200 import cabi
+
+    torch.manual_seed(5)
+    ss0 = tuple(s // 2 for s in WS0) if shifted else (0, 0, 0)
+    c, h, w = res
+    l, d = c * h * w, heads * 64
+    qkv = torch.randn(l, 3 * d, device=DEV).to(torch.bfloat16)
+    pad = torch.randn(3 * d, device=DEV).to(torch.bfloat16)
+    full = torch.empty(l, d, device=DEV, dtype=torch.bfloat16)
+    cabi.window_attention(qkv, full, batch=1, res=res, window=WS0, shift=ss0, num_heads=heads, pad_qkv=pad)
+    full_g = full.view(c, h, w, d)
+    halo = 5
+    for r in range(len(splits) - 1):
+        h0, rows = splits[r], splits[r + 1] - splits[r]
+        local, halo_t, idx_own = _slab_views(qkv, res, 3 * d, h0, rows, halo)
+        out = torch.full((c * rows * w, d), float("nan"), device=DEV, dtype=torch.bfloat16)
+        cabi.window_attention(local, out, batch=1, res=res, window=WS0, shift=ss0, num_heads=heads, pad_qkv=pad,
+                              slab=(h0, rows), halo_qkv=halo_t)
+        torch.cuda.synchronize()
+        want = full_g[:, idx_own].reshape(c * rows * w, d)
+        assert torch.equal(out, want), (r, (out.float() - want.float()).abs().max().item())
