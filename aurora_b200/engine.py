@@ -28,7 +28,7 @@ from typing import Optional
 import numpy as np
 import torch
 
-from aurora_b200 import cabi, encodings as E
+from aurora_b200 import cabi, encodings as E, sharding
 from aurora_b200.batch import Batch, Metadata
 from aurora_b200.spec import DYNAMIC_VARS, ModelConfig
 from aurora_b200.stats import atmos_stats_of, level_to_str, surf_stats_of
@@ -63,6 +63,7 @@ class AuroraEngine:
     def __init__(self, cfg: ModelConfig, params: dict[str, torch.Tensor], variant: str = "base",
                  edge_dtype: str = "fp16") -> None:
         self.cfg = cfg
+        self.shard_group = None  # torch.distributed group used by forward(..., sharded=True)
         self.variant = variant
         some = next(iter(params.values()))
         if not some.is_cuda:
@@ -424,7 +425,8 @@ class AuroraEngine:
     # ------------------------------------------------------------------------------------------
     # backbone  (swin3d.py:884-936)
     # ------------------------------------------------------------------------------------------
-    def _block(self, prefix: str, x_f32, x_b16, res, heads: int, shifted: bool, lora_idx, out_b16=None) -> None:
+    def _block(self, prefix: str, x_f32, x_b16, res, heads: int, shifted: bool, lora_idx, out_b16=None,
+               slab=None) -> None:
         """One Swin3DTransformerBlock in place on the fp32 stream (swin3d.py:440-509).  `out_b16`, if
         given, receives the bf16 copy of the block output instead of x_b16 (used to write into a wider
         buffer, e.g. the skip concatenation)."""
@@ -438,7 +440,18 @@ class AuroraEngine:
         hid = self._buffer("bb.h", (l, self._f32(f"{prefix}.mlp.fc1.bias").numel()), torch.bfloat16)
         cabi.gemm(x_b16, wqkv, bias=self._f32(f"{prefix}.attn.qkv.bias"), out_bf16=qkv)
         pad = self._vec(f"{prefix}.pad_qkv", lambda: self._f32(f"{prefix}.attn.qkv.bias").to(torch.bfloat16))
-        cabi.window_attention(qkv, att, batch=1, res=res, window=ws, shift=ss, num_heads=heads, pad_qkv=pad)
+        if slab is None:
+            cabi.window_attention(qkv, att, batch=1, res=res, window=ws, shift=ss, num_heads=heads, pad_qkv=pad)
+        else:
+            # latitude band of a sharded forecast: swap HALO rows of qkv with both neighbours, then attend over
+            # the GLOBAL window grid restricted to the windows touching this band (sharding.py)
+            h_begin, h_global = slab
+            c_, rows_, w_ = res
+            halo = self._buffer("bb.halo", (2, c_, sharding.HALO, w_ * 3 * d), torch.bfloat16)
+            sharding.exchange_halo(qkv.view(c_, rows_, w_ * 3 * d), sharding.HALO, out=halo, group=self.shard_group)
+            cabi.window_attention(qkv, att, batch=1, res=(c_, h_global, w_), window=ws, shift=ss, num_heads=heads,
+                                  pad_qkv=pad, slab=(h_begin, rows_),
+                                  halo_qkv=halo.view(2, c_, sharding.HALO, w_, 3 * d))
         cabi.gemm(att, wproj, bias=self._f32(f"{prefix}.attn.proj.bias"), out_bf16=y)
         sc1, sh1 = self._modulation(f"{prefix}.norm1", d)
         cabi.ln_mod_residual(y, scale=sc1, shift=sh1, residual=x_f32, out_f32=x_f32, out_bf16=x_b16)
@@ -449,7 +462,8 @@ class AuroraEngine:
         cabi.ln_mod_residual(y, scale=sc2, shift=sh2, residual=x_f32, out_f32=x_f32,
                              out_bf16=x_b16 if out_b16 is None else out_b16)
 
-    def _backbone(self, x_f32: torch.Tensor, x_b16: torch.Tensor, patch_res, rollout_step: int) -> torch.Tensor:
+    def _backbone(self, x_f32: torch.Tensor, x_b16: torch.Tensor, patch_res, rollout_step: int,
+                  plan: Optional["sharding.SlabPlan"] = None) -> torch.Tensor:
         """U-Net over the token stream; returns the bf16 (L, 2*D0) concatenation [x | skip0]."""
         cfg = self.cfg
         d0 = cfg.embed_dim
@@ -459,6 +473,8 @@ class AuroraEngine:
                 f"Patch height ({patch_res[0]}) must be divisible by ws[0] ({cfg.window_size[0]})")
         all_res, padded = stage_resolutions(patch_res, n_enc)
         lora_idx = self._lora_index(rollout_step)
+        # (first owned row, global height) of this rank's band at stage i, or None when not sharded
+        slab_of = (lambda i: None) if plan is None else (lambda i: (plan.rows[i][0], plan.global_h[i]))
         l0 = x_f32.shape[0]
         concat = self._buffer("bb.concat", (l0, 2 * d0), self.ed)  # decoder operand type
         skips: list[Optional[torch.Tensor]] = []
@@ -472,7 +488,7 @@ class AuroraEngine:
                 # (swin3d.py:933-935); nothing else reads it because the merge consumes the fp32 stream
                 last0 = i == 0 and j == depth - 1 and n_enc > 1
                 self._block(f"backbone.encoder_layers.{i}.blocks.{j}", cur_f, cur_b, res, cfg.encoder_num_heads[i],
-                            j % 2 == 1, lora_idx, out_b16=concat[:, d0:] if last0 else None)
+                            j % 2 == 1, lora_idx, out_b16=concat[:, d0:] if last0 else None, slab=slab_of(i))
             if i == 0 and (depth == 0 or n_enc == 1):
                 concat[:, d0:].copy_(cur_b)
             skips.append(cur_f)
@@ -497,7 +513,7 @@ class AuroraEngine:
             for j in range(depth):
                 self._block(f"backbone.decoder_layers.{i}.blocks.{j}", cur_f, cur_b, res, cfg.decoder_num_heads[i],
                             j % 2 == 1, lora_idx,
-                            out_b16=concat[:, :d0] if (final and j == depth - 1) else None)
+                            out_b16=concat[:, :d0] if (final and j == depth - 1) else None, slab=slab_of(index))
             if final and depth == 0:
                 concat[:, :d0].copy_(cur_b)
             if not final:
@@ -652,10 +668,33 @@ class AuroraEngine:
     # whole forward  (aurora.py:265-392)
     # ------------------------------------------------------------------------------------------
     @torch.inference_mode()
-    def forward(self, batch: Batch) -> Batch:
+    def forward(self, batch: Batch, sharded: bool = False) -> Batch:
+        """One model step.  `sharded=True` (one process per GPU, torch.distributed initialised): this rank
+        computes only its latitude band of the forecast (`sharding.plan_slabs`) and returns that band; the
+        result carries `.slab_plans` for `sharding.gather_bands`."""
         cfg = self.cfg
         batch = batch.type(torch.float32)
         batch = batch.crop(patch_size=cfg.patch_size)
+        plans = plan = None
+        if sharded:
+            import torch.distributed as dist
+
+            world = dist.get_world_size(self.shard_group) if dist.is_initialized() else 1
+            rank = dist.get_rank(self.shard_group) if dist.is_initialized() else 0
+            h_img = batch.spatial_shape[0]
+            plans = sharding.plan_slabs(h_img // cfg.patch_size, len(cfg.encoder_depths), world)
+            plan = plans[rank]
+            r0, nr = plan.image_rows(cfg.patch_size)
+            cut = lambda v: v[..., r0:r0 + nr, :]  # noqa: E731
+            lat = batch.metadata.lat
+            batch = Batch(
+                surf_vars={k: cut(v) for k, v in batch.surf_vars.items()},
+                static_vars={k: cut(v) for k, v in batch.static_vars.items()},
+                atmos_vars={k: cut(v) for k, v in batch.atmos_vars.items()},
+                metadata=Metadata(lat=lat[r0:r0 + nr] if lat.dim() == 1 else lat[r0:r0 + nr, :],
+                                  lon=batch.metadata.lon, time=batch.metadata.time,
+                                  atmos_levels=batch.metadata.atmos_levels, rollout_step=batch.metadata.rollout_step),
+            )
         batch = batch.to(self.device)
         batch = dataclasses.replace(
             batch,
@@ -691,10 +730,12 @@ class AuroraEngine:
         x_b16 = self._buffer("xb0", (l_tot, d0), torch.bfloat16)
         for b in range(bsz):
             self._encode(batch, b, x_f32, x_b16)
-            xdec = self._backbone(x_f32, x_b16, patch_res, step)
+            xdec = self._backbone(x_f32, x_b16, patch_res, step, plan)
             self._decode(xdec, batch, b, patch_res, out_surf, out_atmos, step + 1)
 
-        return Batch(
+        if sharded and bsz != 1:
+            raise NotImplementedError("sharded forward supports batch size 1")
+        pred = Batch(
             surf_vars=out_surf,
             static_vars=dict(batch.static_vars),
             atmos_vars=out_atmos,
@@ -706,3 +747,6 @@ class AuroraEngine:
                 rollout_step=step + 1,
             ),
         )
+        if sharded:
+            pred.slab_plans = plans
+        return pred

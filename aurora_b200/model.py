@@ -118,10 +118,14 @@ class Aurora(nn.Module):
             self._engine_sig = sig
         return self._engine
 
-    def forward(self, batch: Batch) -> Batch:
-        """Forward pass: one model time step (`aurora.py:265-392`)."""
+    def forward(self, batch: Batch, sharded: bool = False) -> Batch:
+        """Forward pass: one model time step (`aurora.py:265-392`).
+
+        `sharded=True` (one process per GPU under `torch.distributed`): every rank passes the same batch and
+        gets back ITS latitude band of the prediction (see `aurora_b200/sharding.py`; `gather_bands` rebuilds
+        full fields)."""
         batch = self.batch_transform_hook(batch)
-        return self._get_engine().forward(batch)
+        return self._get_engine().forward(batch, sharded=sharded)
 
     def batch_transform_hook(self, batch: Batch) -> Batch:
         return batch

@@ -1,0 +1,106 @@
+"""Latitude sharding of ONE forecast over the GPUs of a node.
+
+Every rank owns a contiguous band of latitude token rows at every U-Net stage.  Row-wise work (all GEMMs,
+adaLN, MLP, Perceiver encoder / decoder, patch merge / split, patch I/O) touches only local rows.  Window
+attention is the only exchange step: before each attention call the ranks swap `HALO` rows of the qkv
+projection with both neighbours (cyclic in latitude, because the shifted windows wrap), every rank then
+computes all windows touching its band (boundary windows are computed on both sides) and writes only its own
+rows — one send + one receive per neighbour per block, no all-reduce anywhere.
+"""
+
+from __future__ import annotations
+
+import dataclasses
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+__all__ = ["HALO", "SlabPlan", "plan_slabs", "exchange_halo", "gather_bands"]
+
+HALO = 5  # window height 6: a window reaches at most 5 rows into a neighbouring band
+
+
+@dataclasses.dataclass(frozen=True)
+class SlabPlan:
+    """Row ranges of one rank.  `rows[s] = (start, count)` in token rows of U-Net stage `s`."""
+
+    rank: int
+    world: int
+    rows: tuple[tuple[int, int], ...]
+    global_h: tuple[int, ...]  # global token rows per stage
+
+    def image_rows(self, patch: int) -> tuple[int, int]:
+        s, c = self.rows[0]
+        return s * patch, c * patch
+
+
+def plan_slabs(h0: int, n_stages: int, world: int) -> list[SlabPlan]:
+    """Split `h0` stage-0 token rows into `world` bands whose sizes are multiples of 2^(n_stages-1), so that
+    every 2x2 patch merge / split stays inside a band; bands differ by at most one unit."""
+    unit = 2 ** (n_stages - 1)
+    if h0 % unit != 0:
+        raise NotImplementedError(
+            f"latitude sharding needs the token grid height ({h0}) to be a multiple of {unit} "
+            f"(no odd-size patch merging inside the U-Net)")
+    n_units = h0 // unit
+    if n_units < world:
+        raise ValueError(f"cannot split {h0} token rows over {world} ranks")
+    base, rem = divmod(n_units, world)
+    if base < HALO:
+        raise ValueError(
+            f"bands would own {base} rows at the deepest stage, fewer than the {HALO}-row halo their neighbours need; "
+            f"use at most {n_units // HALO} ranks")
+    plans, start = [], 0
+    for r in range(world):
+        cnt = (base + (1 if r < rem else 0)) * unit
+        rows = tuple((start // 2**s, cnt // 2**s) for s in range(n_stages))
+        plans.append(SlabPlan(r, world, rows, tuple(h0 // 2**s for s in range(n_stages))))
+        start += cnt
+    return plans
+
+
+def exchange_halo(local: torch.Tensor, halo: int, out: Optional[torch.Tensor] = None, group=None) -> torch.Tensor:
+    """`local` is one rank's band `[C, rows, X]` (X = W * channels, contiguous).  Returns `[2, C, halo, X]`:
+    index 0 = the `halo` rows just above the band (the previous rank's last rows), index 1 = the rows just
+    below (the next rank's first rows); bands are cyclic neighbours.  One send + one receive per neighbour."""
+    c, rows, x = local.shape
+    assert rows >= halo, f"band of {rows} rows cannot serve a {halo}-row halo"
+    if out is None:
+        out = torch.empty(2, c, halo, x, dtype=local.dtype, device=local.device)
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    first = local[:, :halo].contiguous()
+    last = local[:, rows - halo:].contiguous()
+    if world == 1:
+        out[0].copy_(last)
+        out[1].copy_(first)
+        return out
+    rank = dist.get_rank(group)
+    prev, nxt = (rank - 1) % world, (rank + 1) % world
+    # Posting order matters when prev == nxt (two ranks): the peer posts (first -> me, last -> me), so receive in
+    # the same order: its first rows are my bottom halo, its last rows my top halo.
+    ops = [
+        dist.P2POp(dist.isend, first, prev, group),
+        dist.P2POp(dist.isend, last, nxt, group),
+        dist.P2POp(dist.irecv, out[1], nxt, group),
+        dist.P2POp(dist.irecv, out[0], prev, group),
+    ]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    return out
+
+
+def gather_bands(local: torch.Tensor, plans: list[SlabPlan], patch: int, dim: int = -2, group=None) -> torch.Tensor:
+    """All-gather the latitude bands of an output field (dimension `dim` = latitude) into the full field."""
+    world = len(plans)
+    if world == 1:
+        return local
+    sizes = [p.image_rows(patch)[1] for p in plans]
+    dim = dim % local.dim()
+    pieces = []
+    for p, n in zip(plans, sizes):
+        shape = list(local.shape)
+        shape[dim] = n
+        pieces.append(torch.empty(shape, dtype=local.dtype, device=local.device))
+    dist.all_gather(pieces, local.contiguous(), group=group)
+    return torch.cat(pieces, dim=dim)
