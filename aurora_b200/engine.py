@@ -64,6 +64,8 @@ class AuroraEngine:
                  edge_dtype: str = "fp16") -> None:
         self.cfg = cfg
         self.shard_group = None  # torch.distributed group used by forward(..., sharded=True)
+        self.use_cuda_graph = False  # replay the step from a captured CUDA graph (outputs become static buffers)
+        self._graphs: dict = {}
         self.variant = variant
         some = next(iter(params.values()))
         if not some.is_cuda:
@@ -270,9 +272,14 @@ class AuroraEngine:
         return f
 
     def _combiner(self, group: str, name: str):
-        w = self.p[f"{group}.{name}.weight"].detach().float().cpu().reshape(-1)
-        b = self.p[f"{group}.{name}.bias"].detach().float().cpu().reshape(-1)
-        return float(w[0]), float(w[1]), float(b[0])
+        key = ("combiner", group, name)
+        c = self._w.get(key)
+        if c is None:  # three scalars, read back once (a device->host copy would break stream capture)
+            w = self.p[f"{group}.{name}.weight"].detach().float().cpu().reshape(-1)
+            b = self.p[f"{group}.{name}.bias"].detach().float().cpu().reshape(-1)
+            c = (float(w[0]), float(w[1]), float(b[0]))
+            self._w[key] = c
+        return c
 
     def _surf_transform(self, name: str):
         cfg = self.cfg
@@ -297,8 +304,19 @@ class AuroraEngine:
             float(np.cos(2 * np.pi * tm.day / 365.25)), float(np.sin(2 * np.pi * tm.day / 365.25)),
         ]
 
-    def _encode(self, batch: Batch, b: int, x_f32: torch.Tensor, x_b16: torch.Tensor) -> None:
-        """Fill x (4L, D) for batch element `b`.  `batch` holds physical-unit CUDA fp32 fields, cropped."""
+    def _abs_time_embedding(self, times) -> torch.Tensor:
+        """absolute_time_embed(absolute_time_expansion(t)) per batch element, (B, D) f32 (encoder.py:358-363).
+        Host part (float64 Fourier expansion of `datetime.timestamp() / 3600`, like the reference) + a small
+        fp32 linear on the device; kept outside the CUDA-graph-captured region."""
+        d0 = self.cfg.embed_dim
+        abs_h = torch.tensor([tm.timestamp() / 3600 for tm in times], dtype=torch.float32)
+        abs_enc = E.fourier_expansion(abs_h, d0, E.ABS_TIME_RANGE, assert_range=False).to(self.device)
+        return cabi.linear_small(abs_enc, self._f32("encoder.absolute_time_embed.weight"),
+                                 self._f32("encoder.absolute_time_embed.bias"))
+
+    def _encode(self, batch: Batch, b: int, x_f32: torch.Tensor, x_b16: torch.Tensor, abs_emb: torch.Tensor) -> None:
+        """Fill x (4L, D) for batch element `b`.  `batch` holds physical-unit CUDA fp32 fields, cropped;
+        `abs_emb` is this element's absolute-time embedding (D,)."""
         cfg = self.cfg
         d0, p = cfg.embed_dim, cfg.patch_size
         surf_stats = dict(cfg.surf_stats) if cfg.surf_stats else None
@@ -349,11 +367,7 @@ class AuroraEngine:
                   out_bf16=hbuf[:l], act=GELU)
         cabi.gemm(hbuf[:l], self._e16("encoder.surf_mlp.net.2.weight"), bias=self._f32("encoder.surf_mlp.net.2.bias"),
                   out_bf16=mbuf[:l])
-        # time embeddings (encoder.py:351-363); absolute time via datetime.timestamp() like the reference
-        abs_h = torch.tensor([tm.timestamp() / 3600], dtype=torch.float32)
-        abs_enc = E.fourier_expansion(abs_h, d0, E.ABS_TIME_RANGE, assert_range=False).to(self.device)
-        abs_emb = cabi.linear_small(abs_enc, self._f32("encoder.absolute_time_embed.weight"),
-                                    self._f32("encoder.absolute_time_embed.bias"))[0]
+        # lead-time + absolute-time embeddings (encoder.py:351-363)
         tvec = self.lead_emb + abs_emb
         posscale = self._pos_scale_embed(batch.metadata.lat, batch.metadata.lon)
         cabi.ln_mod_residual(mbuf[:l], scale=self._f32("encoder.surf_norm.weight"),
@@ -671,7 +685,18 @@ class AuroraEngine:
     def forward(self, batch: Batch, sharded: bool = False) -> Batch:
         """One model step.  `sharded=True` (one process per GPU, torch.distributed initialised): this rank
         computes only its latitude band of the forecast (`sharding.plan_slabs`) and returns that band; the
-        result carries `.slab_plans` for `sharding.gather_bands`."""
+        result carries `.slab_plans` for `sharding.gather_bands`.
+
+        With `self.use_cuda_graph` the device work of the step (about 480 kernel launches and, when sharded, 48
+        NCCL halo exchanges) is captured once per input signature and replayed; outputs then live in static
+        buffers that the next call overwrites."""
+        prep = self._prepare(batch, sharded)
+        if self.use_cuda_graph and not self.cfg.dynamic_vars:
+            return self._run_graph(prep)
+        return self._finish(prep, *self._run(prep))
+
+    # -- eager part: dtype / crop / band slicing / H2D, everything that depends on host metadata ----------
+    def _prepare(self, batch: Batch, sharded: bool) -> dict:
         cfg = self.cfg
         batch = batch.type(torch.float32)
         batch = batch.crop(patch_size=cfg.patch_size)
@@ -710,14 +735,26 @@ class AuroraEngine:
         bsz, t_hist = some.shape[:2]
         if t_hist > cfg.max_history_size:
             raise AssertionError(f"{t_hist} > {cfg.max_history_size}.")
+        if sharded and bsz != 1:
+            raise NotImplementedError("sharded forward supports batch size 1")
+        return {"batch": batch, "plan": plan, "plans": plans, "sharded": sharded,
+                "abs_emb": self._abs_time_embedding(batch.metadata.time),
+                "posscale": self._pos_scale_embed(batch.metadata.lat, batch.metadata.lon)}
+
+    # -- device part: only kernel launches on the current stream (capturable) ----------------------------
+    def _run(self, prep: dict):
+        cfg = self.cfg
+        batch, plan = prep["batch"], prep["plan"]
+        h, w = batch.spatial_shape
+        p = cfg.patch_size
+        some = next(iter(batch.surf_vars.values()))
+        bsz = some.shape[0]
         patch_res = (cfg.latent_levels, h // p, w // p)
-        l = patch_res[1] * patch_res[2]
-        l_tot = cfg.latent_levels * l
+        l_tot = cfg.latent_levels * patch_res[1] * patch_res[2]
         d0 = cfg.embed_dim
         levels = tuple(batch.metadata.atmos_levels)
         step = batch.metadata.rollout_step
         air = self.variant == "air_pollution"
-
         surf_out_names = tuple(batch.surf_vars) if air else tuple(batch.surf_vars) + tuple(
             f"{n}_mod" for n in batch.surf_vars if n in cfg.modulation_heads)
         atmos_out_names = tuple(batch.atmos_vars) if air else tuple(batch.atmos_vars) + tuple(
@@ -725,16 +762,16 @@ class AuroraEngine:
         out_surf = {k: torch.empty(bsz, 1, h, w, dtype=torch.float32, device=self.device) for k in surf_out_names}
         out_atmos = {k: torch.empty(bsz, 1, len(levels), h, w, dtype=torch.float32, device=self.device)
                      for k in atmos_out_names}
-
         x_f32 = self._buffer("x0", (l_tot, d0), torch.float32)
         x_b16 = self._buffer("xb0", (l_tot, d0), torch.bfloat16)
         for b in range(bsz):
-            self._encode(batch, b, x_f32, x_b16)
+            self._encode(batch, b, x_f32, x_b16, prep["abs_emb"][b])
             xdec = self._backbone(x_f32, x_b16, patch_res, step, plan)
             self._decode(xdec, batch, b, patch_res, out_surf, out_atmos, step + 1)
+        return out_surf, out_atmos
 
-        if sharded and bsz != 1:
-            raise NotImplementedError("sharded forward supports batch size 1")
+    def _finish(self, prep: dict, out_surf: dict, out_atmos: dict) -> Batch:
+        batch = prep["batch"]
         pred = Batch(
             surf_vars=out_surf,
             static_vars=dict(batch.static_vars),
@@ -742,11 +779,50 @@ class AuroraEngine:
             metadata=Metadata(
                 lat=batch.metadata.lat,
                 lon=batch.metadata.lon,
-                time=tuple(tm + cfg.timestep for tm in batch.metadata.time),
+                time=tuple(tm + self.cfg.timestep for tm in batch.metadata.time),
                 atmos_levels=batch.metadata.atmos_levels,
-                rollout_step=step + 1,
+                rollout_step=batch.metadata.rollout_step + 1,
             ),
         )
-        if sharded:
-            pred.slab_plans = plans
+        if prep["sharded"]:
+            pred.slab_plans = prep["plans"]
         return pred
+
+    # -- CUDA-graph replay --------------------------------------------------------------------------------
+    def _run_graph(self, prep: dict) -> Batch:
+        batch = prep["batch"]
+        step = batch.metadata.rollout_step
+        sig = (
+            tuple((k, tuple(v.shape)) for k, v in batch.surf_vars.items()),
+            tuple((k, tuple(v.shape)) for k, v in batch.static_vars.items()),
+            tuple((k, tuple(v.shape)) for k, v in batch.atmos_vars.items()),
+            tuple(batch.metadata.atmos_levels), self._lora_index(step), min(step, 2), prep["sharded"],
+            None if prep["plan"] is None else prep["plan"].rows,
+        )
+        entry = self._graphs.get(sig)
+        if entry is None:
+            # static input buffers (the captured launches bake device pointers), one eager warm-up, then capture
+            static = Batch(
+                surf_vars={k: v.clone() for k, v in batch.surf_vars.items()},
+                static_vars={k: v.clone() for k, v in batch.static_vars.items()},
+                atmos_vars={k: v.clone() for k, v in batch.atmos_vars.items()},
+                metadata=batch.metadata,
+            )
+            sprep = dict(prep, batch=static, abs_emb=prep["abs_emb"].clone())
+            self._run(sprep)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                outs = self._run(sprep)
+            entry = {"graph": graph, "prep": sprep, "outs": outs}
+            self._graphs[sig] = entry
+        sprep = entry["prep"]
+        sb = sprep["batch"]
+        for dst, src in ((sb.surf_vars, batch.surf_vars), (sb.static_vars, batch.static_vars),
+                         (sb.atmos_vars, batch.atmos_vars)):
+            for k, v in src.items():
+                if dst[k].data_ptr() != v.data_ptr():
+                    dst[k].copy_(v)
+        sprep["abs_emb"].copy_(prep["abs_emb"])
+        entry["graph"].replay()
+        return self._finish(prep, *entry["outs"])

@@ -91,6 +91,10 @@ class Aurora(nn.Module):
                 self._put(key, value)
         self._engine = None
         self._engine_sig = None
+        self.use_cuda_graph = False
+        """bool: replay each forward step from a captured CUDA graph (one capture per input signature).
+        Predictions then live in static device buffers that the next `forward` overwrites — copy what you keep
+        (`rollout` does, `pred.to("cpu")` does)."""
 
     # -- parameter tree ---------------------------------------------------------------------------
     def _extra_specs(self):
@@ -116,6 +120,7 @@ class Aurora(nn.Module):
                     f"parameters of dtype {p0.dtype} are not supported")
             self._engine = AuroraEngine(self.config, {k: v.data for k, v in params.items()}, variant=self._variant)
             self._engine_sig = sig
+        self._engine.use_cuda_graph = bool(self.use_cuda_graph)
         return self._engine
 
     def forward(self, batch: Batch, sharded: bool = False) -> Batch:

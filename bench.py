@@ -274,6 +274,7 @@ def main() -> None:
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--parallelism", default="replicas", choices=["replicas", "latshard"],
                     help="N > 1: independent forecasts per GPU (default) or ONE forecast sharded by latitude")
+    ap.add_argument("--cuda-graph", action="store_true", help="model.use_cuda_graph = True (step replayed from a graph)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -300,6 +301,7 @@ def main() -> None:
     cls, h, w, levels = WORKLOADS[args.workload]
     model = getattr(ab, cls)(_init="empty").to(dev).eval()
     randomise_parameters_(model, seed=rank)
+    model.use_cuda_graph = bool(args.cuda_graph)
     cfg = model.config
     host_batch = make_host_batch(cfg, h, w, levels, pinned=True, seed=rank)
     dev_batch = host_batch.to(dev)
@@ -359,6 +361,7 @@ def main() -> None:
 
     # ---- per-kernel timing for the roofline (one instrumented step; CUDA events around each launch) ----
     cabi.PROFILE = {}
+    model.use_cuda_graph = False
     model.forward(dev_batch)
     torch.cuda.synchronize()
     prof = cabi.PROFILE
@@ -420,6 +423,7 @@ def main() -> None:
                                 if latshard else f"replicas x{world}") if world > 1 else "single GPU",
                 "l2_note": "inputs and activations are GBs per step (>> 126 MB L2); no explicit flush needed",
                 "algorithmic_tflop_per_step": algo_tflop,
+                "cuda_graph": bool(args.cuda_graph),
             },
             "model_tflops_achieved": algo_tflop / (ms / 1e3),
             "clocks": clocks,

@@ -97,3 +97,18 @@ def test_no_cpu_path():
     model = ab.Aurora(**fx.reference_kwargs(cfg))
     with pytest.raises(RuntimeError, match="CUDA"):
         model.forward(fx.make_batch(cfg, 17, 32, levels=fx.LEVELS4))
+
+
+def test_cuda_graph_replay_is_bit_identical_to_eager():
+    """`model.use_cuda_graph`: capture once, replay on new inputs; same bits as the eager launches."""
+    cfg, model = _build("tiny_lora", "Aurora", 13)
+    b1 = fx.make_batch(cfg, 33, 64, levels=fx.LEVELS4, b=1, seed=13)
+    b2 = fx.make_batch(cfg, 33, 64, levels=fx.LEVELS4, b=1, seed=14)
+    e1 = {k: v.clone() for k, v in model.forward(b1).atmos_vars.items()}
+    e2 = {k: v.clone() for k, v in model.forward(b2).atmos_vars.items()}
+    model.use_cuda_graph = True
+    g1 = {k: v.clone() for k, v in model.forward(b1).atmos_vars.items()}   # capture
+    g2 = {k: v.clone() for k, v in model.forward(b2).atmos_vars.items()}   # replay with other inputs
+    g1b = {k: v.clone() for k, v in model.forward(b1).atmos_vars.items()}  # replay again
+    for k in e1:
+        assert torch.equal(e1[k], g1[k]) and torch.equal(e2[k], g2[k]) and torch.equal(e1[k], g1b[k]), k
