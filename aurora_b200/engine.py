@@ -221,10 +221,12 @@ class AuroraEngine:
     def _pos_scale_embed(self, lat: torch.Tensor, lon: torch.Tensor) -> torch.Tensor:
         """pos_embed(pos_enc) + scale_embed(scale_enc), (L, D) f32 (encoder.py:334-346); cached per grid."""
         c = self._grid_cache
-        if c is not None and c[0].shape == lat.shape and c[1].shape == lon.shape and (
-            (c[0] is lat and c[1] is lon) or (torch.equal(c[0], lat) and torch.equal(c[1], lon))
-        ):
-            return c[2]
+        if c is not None and c[0].shape == lat.shape and c[1].shape == lon.shape:
+            if c[0] is lat and c[1] is lon:
+                return c[2]
+            if torch.equal(c[0], lat) and torch.equal(c[1], lon):  # same grid, new tensor objects
+                self._grid_cache = (lat, lon, c[2])
+                return c[2]
         d0 = self.cfg.embed_dim
         pos, scale = E.pos_scale_encodings(d0, lat.detach().float().cpu(), lon.detach().float().cpu(), self.cfg.patch_size)
         pos, scale = pos.to(self.device), scale.to(self.device)
@@ -314,7 +316,8 @@ class AuroraEngine:
         return cabi.linear_small(abs_enc, self._f32("encoder.absolute_time_embed.weight"),
                                  self._f32("encoder.absolute_time_embed.bias"))
 
-    def _encode(self, batch: Batch, b: int, x_f32: torch.Tensor, x_b16: torch.Tensor, abs_emb: torch.Tensor) -> None:
+    def _encode(self, batch: Batch, b: int, x_f32: torch.Tensor, x_b16: torch.Tensor, abs_emb: torch.Tensor,
+                posscale: torch.Tensor) -> None:
         """Fill x (4L, D) for batch element `b`.  `batch` holds physical-unit CUDA fp32 fields, cropped;
         `abs_emb` is this element's absolute-time embedding (D,)."""
         cfg = self.cfg
@@ -369,7 +372,6 @@ class AuroraEngine:
                   out_bf16=mbuf[:l])
         # lead-time + absolute-time embeddings (encoder.py:351-363)
         tvec = self.lead_emb + abs_emb
-        posscale = self._pos_scale_embed(batch.metadata.lat, batch.metadata.lon)
         cabi.ln_mod_residual(mbuf[:l], scale=self._f32("encoder.surf_norm.weight"),
                              shift=(self._f32("encoder.surf_norm.bias") + tvec).contiguous(), residual=xs0,
                              add_rows=posscale, out_f32=x_f32[:l], out_bf16=x_b16[:l])
@@ -765,7 +767,7 @@ class AuroraEngine:
         x_f32 = self._buffer("x0", (l_tot, d0), torch.float32)
         x_b16 = self._buffer("xb0", (l_tot, d0), torch.bfloat16)
         for b in range(bsz):
-            self._encode(batch, b, x_f32, x_b16, prep["abs_emb"][b])
+            self._encode(batch, b, x_f32, x_b16, prep["abs_emb"][b], prep["posscale"])
             xdec = self._backbone(x_f32, x_b16, patch_res, step, plan)
             self._decode(xdec, batch, b, patch_res, out_surf, out_atmos, step + 1)
         return out_surf, out_atmos
