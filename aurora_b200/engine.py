@@ -693,7 +693,9 @@ class AuroraEngine:
         NCCL halo exchanges) is captured once per input signature and replayed; outputs then live in static
         buffers that the next call overwrites."""
         prep = self._prepare(batch, sharded)
-        if self.use_cuda_graph and not self.cfg.dynamic_vars:
+        # Graph replay is single-GPU only: capturing the NCCL point-to-point halo exchange deadlocked on the
+        # test pod (torch 2.11 / NCCL 2.28), so sharded steps always launch eagerly.
+        if self.use_cuda_graph and not self.cfg.dynamic_vars and not sharded:
             return self._run_graph(prep)
         return self._finish(prep, *self._run(prep))
 
