@@ -72,7 +72,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
     }
     if (g.act == AB_ACT_GELU_ERF) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+      for (int j = 0; j < 32; j += 2) gelu_erf_x2(f[j], f[j + 1]);
     }
     if (g.residual != nullptr) {
       const float4* r4 = reinterpret_cast<const float4*>(g.residual + static_cast<size_t>(row) * g.ldr + col0);
@@ -139,10 +139,8 @@ __device__ __forceinline__ void epilogue_stage_half(const GemmArgs& g, const uin
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 b = __ldg(b4 + j);
-        f[4 * j + 0] += b.x;
-        f[4 * j + 1] += b.y;
-        f[4 * j + 2] += b.z;
-        f[4 * j + 3] += b.w;
+        f32x2_unpack(f32x2_add(f32x2_pack(f[4 * j + 0], f[4 * j + 1]), f32x2_pack(b.x, b.y)), f[4 * j + 0], f[4 * j + 1]);
+        f32x2_unpack(f32x2_add(f32x2_pack(f[4 * j + 2], f[4 * j + 3]), f32x2_pack(b.z, b.w)), f[4 * j + 2], f[4 * j + 3]);
       }
     } else {
 #pragma unroll
@@ -152,7 +150,7 @@ __device__ __forceinline__ void epilogue_stage_half(const GemmArgs& g, const uin
   }
   if (g.act == AB_ACT_GELU_ERF) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+    for (int j = 0; j < 32; j += 2) gelu_erf_x2(f[j], f[j + 1]);
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -588,6 +586,269 @@ static int launch_gemm2(const AbGemm* p, const GemmArgs& args, cudaStream_t stre
   return AB_OK;
 }
 
+
+// ================================================================================================
+// Wide CTA-pair variant: one 512 x 256 output tile per cluster of two CTAs (256 x 256 per CTA).
+//
+// ncu on the 256 x 256 pair kernel shows the large-K GEMMs of this model are bound by L2 -> SM delivery, not by
+// the tensor pipe: l1tex__m_xbar2l1tex_read_bytes / duration = 10.8 TB/s = 6.6 KB/clk chip-wide, the LTS cap
+// (profiles/r01_ncu_full_summaries.md, r01j; cuBLAS' nvjet 256x256-per-CTA kernel moves 0.75x the bytes).  Staging
+// 256 rows of A per CTA against the same half W tile cuts operand bytes per flop by 25 %:
+//   per k-block and CTA: A 2 x (128 x 64) + W 128 x 64 = 48 KB for two M=256 MMAs (was 32 KB for one).
+// The two accumulators (one per 128-row half, 256 fp32 columns each) fill all 512 TMEM columns, so there is no
+// spare accumulator to double-buffer with.  Instead the MMA issuer staggers the two accumulators at the tile
+// boundaries only: acc 0 takes the last kLag k-blocks of a tile before acc 1 does, so acc 0 finishes first and the
+// epilogue warps drain it while the tensor pipe finishes acc 1; the next tile starts with kLag k-blocks on acc 0,
+// which cover the drain of acc 1.  In between both advance in lockstep so that all 4 stages (192 KB) stay in
+// flight — a permanently lagging acc 1 (tried first) pins kLag stages and starves the L2-latency-bound loads.
+// Used for plain (no activation) epilogues with K >= 1024, where a drain is short against the main loop.
+// ================================================================================================
+template <bool kHalfIn>
+struct Gemm2wCfg {
+  static constexpr int BN = 256;
+  static constexpr int kLoadN = 128;
+  static constexpr int kSubA = kBlockM * kBlockK * 2;         // one 128-row half of A: 16 KB
+  static constexpr int kStageBytesA = 2 * kSubA;
+  static constexpr int kStageBytesB = kLoadN * kBlockK * 2;
+  static constexpr int kStageBytes = kStageBytesA + kStageBytesB;  // 48 KB
+  static constexpr int kStages = 4;
+  static constexpr int kLag = 2;  // k-blocks accumulator 0 leads by at the tile boundaries
+  static constexpr uint32_t kTmemCols = 2 * BN;
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kStagingBytes = kNumEpiWarps * 4096;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024;
+};
+
+template <bool kHalfIn>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+gemm2w_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                      const __grid_constant__ CUtensorMap tmap_out, const GemmArgs g) {
+  using Cfg = Gemm2wCfg<kHalfIn>;
+  constexpr int BN = Cfg::BN;
+  constexpr int kTileM = 4 * kBlockM;  // 512 rows per cluster tile
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kStageBytesA;
+  uint8_t* smem_stage_out = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stage_out + Cfg::kStagingBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;  // [h]: accumulator h holds a finished tile
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [h]: accumulator h has been read out (leader's)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  cluster_sync_all();
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_w);
+    if (g.tma_out) prefetch_tmap(&tmap_out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 2);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(&tmem_full_bar[h], 1);
+      mbar_init(&tmem_empty_bar[h], 2 * kNumEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before_sync();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_n = (g.n + BN - 1) / BN;
+  const int num_mt = (g.m + kTileM - 1) / kTileM;
+  const int num_tiles = num_mt * num_n;
+  const int num_kb = (g.k + kBlockK - 1) / kBlockK;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs): rows [m0, m0 + 256) of A as two 128-row boxes, 128 rows of W =====
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile / num_n) * kTileM + rank * (2 * kBlockM);
+        const int n0 = (tile % num_n) * BN + rank * Cfg::kLoadN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* sa = smem_a + s * Cfg::kStageBytesA;
+          tma_load_2d_pair(sa, &tmap_a, &full_bar[s], kb * kBlockK, m0);
+          tma_load_2d_pair(sa + Cfg::kSubA, &tmap_a, &full_bar[s], kb * kBlockK, m0 + kBlockM);
+          tma_load_2d_pair(smem_b + s * Cfg::kStageBytesB, &tmap_w, &full_bar[s], kb * kBlockK, n0);
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);
+          else mbar_arrive_remote(&full_bar[s], 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ===== MMA issuer (leader CTA only) =====
+      // Issue order per tile: the two accumulators advance in lockstep (all stages stay in flight), except that
+      // accumulator 0 takes the first and the last kLag k-blocks of the tile ahead of accumulator 1 — see above.
+      constexpr uint32_t idesc = umma_idesc_f16kind_f32(2 * kBlockM, BN, kHalfIn);
+      uint32_t base_it = 0, tc = 0;  // k-blocks consumed before this tile
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tc) {
+        const uint32_t tph = tc & 1u;
+        auto issue = [&](int h, int kb) {
+          const uint32_t it = base_it + kb;
+          const uint32_t s = it % Cfg::kStages;
+          if (kb == 0) mbar_wait(&tmem_empty_bar[h], tph ^ 1u);
+          if (h == 0) mbar_wait(&full_bar[s], (it / Cfg::kStages) & 1u);  // acc 1 always follows acc 0 on a stage
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem_a + s * Cfg::kStageBytesA + h * Cfg::kSubA);
+          const uint32_t b_addr = smem_u32(smem_b + s * Cfg::kStageBytesB);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_bf16_ss_pair(tmem_base + h * BN, umma_desc_k_sw128(a_addr + k * kUmmaK * 2),
+                              umma_desc_k_sw128(b_addr + k * kUmmaK * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          if (h == 1) umma_commit_pair(&empty_bar[s]);  // both halves of the stage are consumed
+          if (kb == num_kb - 1) umma_commit_pair(&tmem_full_bar[h]);
+        };
+        constexpr int X = Cfg::kLag;
+        if (X > 0 && num_kb >= 2 * X) {
+          for (int kb = 0; kb < X; ++kb) issue(0, kb);
+          for (int kb = 0; kb < X; ++kb) issue(1, kb);
+          for (int kb = X; kb < num_kb - X; ++kb) {
+            issue(0, kb);
+            issue(1, kb);
+          }
+          for (int kb = num_kb - X; kb < num_kb; ++kb) issue(0, kb);
+          for (int kb = num_kb - X; kb < num_kb; ++kb) issue(1, kb);
+        } else {
+          for (int kb = 0; kb < num_kb; ++kb) {
+            issue(0, kb);
+            issue(1, kb);
+          }
+        }
+        base_it += num_kb;
+      }
+      // Let the last remote arrivals land on our barriers before the CTA may exit.
+      if (tc > 0) {
+        const uint32_t last = tc - 1;
+        mbar_wait(&tmem_empty_bar[0], last & 1u);
+        mbar_wait(&tmem_empty_bar[1], last & 1u);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: accumulator 0 (rows +0..127 of this CTA's 256), then accumulator 1 (rows +128..255) =====
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    uint32_t tc = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tc) {
+      const int n0 = (tile % num_n) * BN;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int m0 = (tile / num_n) * kTileM + rank * (2 * kBlockM) + h * kBlockM;
+        mbar_wait(&tmem_full_bar[h], tc & 1u);
+        tc_fence_after_sync();
+        const int row = m0 + q * 32 + lane;
+        const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * BN;
+        if (g.tma_out) {
+          uint8_t* stage = smem_stage_out + (warp - 4) * 4096;
+          const uint32_t stage_row = smem_u32(stage) + lane * 128;
+#pragma unroll 1
+          for (int c = half * 64; c < BN; c += 128) {
+            const bool live = n0 + c < g.n;
+            const bool last = c + 128 >= BN;
+            uint32_t v0[32], v1[32];
+            tmem_ld_32x32b_x32(tacc + c, v0);
+            tmem_ld_32x32b_x32(tacc + c + 32, v1);
+            tmem_ld_wait();
+            if (last) {
+              // everything this warp needs from the accumulator is in registers: hand it back before the math
+              tc_fence_before_sync();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[h], 0);
+            }
+            if (!live) continue;
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+            epilogue_stage_half<BN>(g, v0, n0 + c, stage_row, lane, 0);
+            epilogue_stage_half<BN>(g, v1, n0 + c + 32, stage_row, lane, 4);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && m0 + q * 32 < g.m) {
+              tma_store_2d(&tmap_out, stage, n0 + c, m0 + q * 32);
+              tma_store_commit();
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tacc + c, v);
+            tmem_ld_wait();
+            epilogue_chunk<BN>(g, v, row, n0 + c);
+          }
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[h], 0);
+        }
+      }
+    }
+  }
+
+  if (warp >= 4 && g.tma_out && lane == 0) tma_store_wait_all<0>();
+  __syncwarp();
+  tc_fence_before_sync();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <bool kHalfIn>
+static int launch_gemm2w(const AbGemm* p, const GemmArgs& args, cudaStream_t stream) {
+  using Cfg = Gemm2wCfg<kHalfIn>;
+  CUtensorMap ta, tw;
+  int rc = make_tmap_16bit_2d(&ta, p->a, p->m, p->k, p->lda, kBlockM, kBlockK, kHalfIn);
+  if (rc != AB_OK) return rc;
+  rc = make_tmap_16bit_2d(&tw, p->w, p->n, p->k, p->ldw, Cfg::kLoadN, kBlockK, kHalfIn);
+  if (rc != AB_OK) return rc;
+  CUtensorMap tout = ta;
+  if (args.tma_out) {
+    rc = make_tmap_16bit_2d(&tout, p->out_bf16, p->m, p->n, p->ld_bf16, 32, 64, args.out_half != 0);
+    if (rc != AB_OK) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2w_bf16_tn_kernel<kHalfIn>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("ab_gemm_bf16: cudaFuncSetAttribute(wide pair, smem=%d) failed: %s", Cfg::kSmemBytes,
+                cudaGetErrorString(e));
+      return AB_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const long long tiles = ceil_div_ll(p->m, 4 * kBlockM) * ceil_div_ll(p->n, Cfg::BN);
+  const long long max_clusters = sm_count() / 2;
+  const int clusters = static_cast<int>(tiles < max_clusters ? tiles : max_clusters);
+  gemm2w_bf16_tn_kernel<kHalfIn><<<2 * clusters, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tw, tout, args);
+  AB_COUNT_LAUNCH(1);
+  AB_CHECK_LAUNCH("ab_gemm_bf16(wide pair)");
+  return AB_OK;
+}
+
+// Wave efficiency of a persistent launch: useful tiles / (waves x resident clusters).
+static double wave_efficiency(long long tiles, long long slots) {
+  const long long waves = (tiles + slots - 1) / slots;
+  return static_cast<double>(tiles) / static_cast<double>(waves * slots);
+}
+
 }  // namespace ab
 
 extern "C" int ab_gemm_bf16(const AbGemm* p, void* stream) {
@@ -632,6 +893,20 @@ extern "C" int ab_gemm_bf16(const AbGemm* p, void* stream) {
   // Large problems run on CTA pairs (cta_group::2); small or narrow ones on the single-CTA kernel.
   static const bool pair_disabled = getenv("AB_GEMM_NO_PAIR") != nullptr;
   if (!pair_disabled && p->n >= 256 && p->m >= 1024) {
+    // 512 x 256 tiles (25 % fewer operand bytes through the L2 -> SM path) pay off when the main loop is long
+    // against the accumulator drain (K >= 2048, plain epilogue) and the coarser tiles do not cost a wave:
+    // measured -5 % (259200 x 512 x 2048) and -9 % (64800 x 1024 x 4096), neutral at K = 1024
+    // (profiles/r01_kernel_probes.md).  AB_GEMM_WIDE: 0 = never, 2 = whenever K >= 1024 (tests).
+    const char* wide_env = getenv("AB_GEMM_WIDE");  // read per call so that tests can flip it
+    const int wide_mode = wide_env ? atoi(wide_env) : 1;
+    bool wide = false;
+    if (wide_mode > 0 && p->k >= 1024) {
+      const long long slots = sm_count() / 2;
+      const double eff_w = wave_efficiency(ceil_div_ll(p->m, 4 * kBlockM) * ceil_div_ll(p->n, 256), slots);
+      const double eff_2 = wave_efficiency(ceil_div_ll(p->m, 2 * kBlockM) * ceil_div_ll(p->n, 256), slots);
+      wide = wide_mode >= 2 || (p->act == AB_ACT_NONE && p->k >= 2048 && eff_w * 1.02 >= eff_2);
+    }
+    if (wide) return p->in_dtype == AB_DT_F16 ? launch_gemm2w<true>(p, a, s) : launch_gemm2w<false>(p, a, s);
     return p->in_dtype == AB_DT_F16 ? launch_gemm2<true>(p, a, s) : launch_gemm2<false>(p, a, s);
   }
   if (p->in_dtype == AB_DT_F16) {

@@ -4,7 +4,6 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
-#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -363,6 +362,53 @@ __device__ __forceinline__ float gelu_erf(float x) {
   r = fmaf(r, z, -0.5599349141120911f);
   r = fmaf(r, z, 0.49980518221855164f);
   return fmaf(-fabsf(x), e * r, fmaxf(x, 0.f));
+}
+
+// Two GELUs at once on the packed fp32 pipe (fma / mul .f32x2, sm_100+): same polynomial and rounding as
+// gelu_erf, 9 instead of 14.5 issue slots per element.  The K = 512 fc1 epilogue is bound by the issue slots
+// of its 8 epilogue warps (profiles/r01_ncu_full_summaries.md, r01h), so this is what the tensor pipe waits for.
+__device__ __forceinline__ uint64_t f32x2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f32x2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f32x2_splat(float c) { return f32x2_pack(c, c); }
+
+__device__ __forceinline__ void gelu_erf_x2(float& x0, float& x1) {
+  const float na0 = -fabsf(x0), na1 = -fabsf(x1);
+  const float z0 = fminf(na0 * -0.70710678118654752440f, 4.5f);
+  const float z1 = fminf(na1 * -0.70710678118654752440f, 4.5f);
+  const uint64_t z = f32x2_pack(z0, z1);
+  float a0, a1, e0, e1;
+  f32x2_unpack(f32x2_mul(f32x2_mul(z, f32x2_splat(-1.4426950408889634f)), z), a0, a1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  uint64_t r = f32x2_fma(f32x2_splat(0.003532303497195244f), z, f32x2_splat(-0.032581403851509094f));
+  r = f32x2_fma(r, z, f32x2_splat(0.12916485965251923f));
+  r = f32x2_fma(r, z, f32x2_splat(-0.29942014813423157f));
+  r = f32x2_fma(r, z, f32x2_splat(0.47322216629981995f));
+  r = f32x2_fma(r, z, f32x2_splat(-0.5599349141120911f));
+  r = f32x2_fma(r, z, f32x2_splat(0.49980518221855164f));
+  const uint64_t er = f32x2_mul(f32x2_pack(e0, e1), r);
+  f32x2_unpack(f32x2_fma(f32x2_pack(na0, na1), er, f32x2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), x0, x1);
 }
 
 }  // namespace ab

@@ -63,6 +63,46 @@ def test_gemm_matches_fp32_reference(m, n, k, mode):
     torch.testing.assert_close(out_bf16.float(), ref, rtol=1e-2, atol=1e-2)
 
 
+WIDE_SHAPES = [
+    (1024, 256, 1024),    # two full 512-row cluster tiles
+    (1500, 520, 1024),    # M tail inside the second CTA's halves, N tail (8 live columns in the last block)
+    (2049, 256, 1088),    # one row into a new tile (three of four 128-row boxes fully out of bounds), odd k-block count
+    (20000, 1536, 1024),  # several tiles per cluster: accumulator hand-over between tiles
+    (4096, 512, 4096),    # long K
+]
+
+
+@pytest.mark.parametrize("m,n,k", WIDE_SHAPES)
+@pytest.mark.parametrize("mode", ["plain_bf16", "bias_gelu_bf16", "bias_res_f32_dual"])
+def test_wide_pair_kernel_matches_reference_and_pair_kernel(m, n, k, mode, monkeypatch):
+    """512 x 256 cluster-tile kernel (AB_GEMM_WIDE=2 forces it): fp32 reference tolerance, and bit-identical to
+    the 256 x 256 pair kernel (same fp32 accumulation order over K)."""
+    from aurora_b200 import cabi
+
+    torch.manual_seed(m + n + k)
+    dev = "cuda"
+    a = torch.randn(m, k, device=dev).to(torch.bfloat16)
+    w = (torch.randn(n, k, device=dev) / k**0.5).to(torch.bfloat16)
+    bias = torch.randn(n, device=dev) if mode != "plain_bf16" else None
+    residual = torch.randn(m, n, device=dev) if mode == "bias_res_f32_dual" else None
+    act = cabi.AB_ACT_GELU_ERF if mode == "bias_gelu_bf16" else cabi.AB_ACT_NONE
+    outs = {}
+    for wide in ("2", "0"):
+        monkeypatch.setenv("AB_GEMM_WIDE", wide)
+        out_bf16 = torch.full((m, n), float("nan"), device=dev, dtype=torch.bfloat16)
+        out_f32 = torch.full((m, n), float("nan"), device=dev) if mode == "bias_res_f32_dual" else None
+        cabi.gemm(a, w, bias=bias, residual=residual, out_f32=out_f32, out_bf16=out_bf16, act=act)
+        torch.cuda.synchronize()
+        outs[wide] = (out_bf16, out_f32)
+    ref = _ref(a, w, bias, residual, act)
+    out_bf16, out_f32 = outs["2"]
+    if out_f32 is not None:
+        torch.testing.assert_close(out_f32, ref, rtol=1e-4, atol=1e-4)
+        assert torch.equal(out_f32, outs["0"][1])
+    torch.testing.assert_close(out_bf16.float(), ref, rtol=1e-2, atol=1e-2)
+    assert torch.equal(out_bf16, outs["0"][0])
+
+
 def test_gemm_strided_views():
     """Leading dimensions larger than the logical width (writes into a slice of a wider buffer)."""
     from aurora_b200 import cabi
