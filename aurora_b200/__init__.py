@@ -10,10 +10,11 @@ from aurora_b200.model import (
     AuroraPretrained,
     AuroraSmall,
     AuroraSmallPretrained,
+    AuroraWave,
 )
 from aurora_b200.rollout import rollout
 
 __all__ = [
     "Aurora", "AuroraPretrained", "AuroraSmallPretrained", "AuroraSmall", "Aurora12hPretrained", "AuroraHighRes",
-    "AuroraAirPollution", "Batch", "Metadata", "rollout",
+    "AuroraAirPollution", "AuroraWave", "Batch", "Metadata", "rollout",
 ]

@@ -101,8 +101,9 @@ EXPORTS = [
     "ab_patchify",
     "ab_unpatchify",
 ]
-AB_MAX_FIELDS = 40
+AB_MAX_FIELDS = 64
 AB_IN_PLAIN, AB_IN_CLAMP_MIN0, AB_IN_CLAMP_LOG_COMBINE = 0, 1, 2
+AB_IN_NAN_TO_ZERO, AB_IN_DENSITY, AB_IN_SIN_DEG, AB_IN_COS_DEG = 3, 4, 5, 6
 
 
 # Optional per-call device timing (bench.py's roofline leg): when PROFILE is a dict, every op wrapper
@@ -266,7 +267,15 @@ class AbFieldOut(C.Structure):
         ("mod_col", C.c_int32),
         ("clamp_min0", C.c_int32),
         ("clamp_max1", C.c_int32),
+        ("cos_col", C.c_int32),
+        ("dens_col", C.c_int32),
+        ("mask", C.c_void_p),
+        ("mask_min", C.c_float),
     ]
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.mod_col = self.cos_col = self.dens_col = -1
 
 
 def _i3(v):

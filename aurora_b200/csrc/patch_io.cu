@@ -22,8 +22,25 @@ struct PatchifyArgs {
   int out_half;
 };
 
+// torch.nan_to_num(v, nan=0): NaN -> 0, +-inf -> +-FLT_MAX
+__device__ __forceinline__ float nan_to_num0(float v) {
+  if (isnan(v)) return 0.f;
+  if (isinf(v)) return v > 0.f ? 3.402823466e+38f : -3.402823466e+38f;
+  return v;
+}
+
 __device__ __forceinline__ float transform_in(const AbFieldIn& f, float x) {
   float v = (x - f.loc) / f.scale;
+  if (f.transform >= AB_IN_NAN_TO_ZERO) {
+    // AuroraWave._pre_encoder_hook (aurora.py:874-892), on the normalised value
+    const float kDegToRad = 0.017453292519943295f;
+    switch (f.transform) {
+      case AB_IN_NAN_TO_ZERO: return nan_to_num0(v);
+      case AB_IN_DENSITY: return isnan(v) ? 0.f : 1.f;
+      case AB_IN_SIN_DEG: return nan_to_num0(sinf(v * kDegToRad));
+      default: return nan_to_num0(cosf(v * kDegToRad));
+    }
+  }
   if (f.transform >= 1) v = fmaxf(v, 0.f);
   if (f.transform == 2) {
     // AuroraAirPollution._pre_encoder_hook: Linear(2,1)([clamp(z,0,2.5), (log(max(z,eps)) - log eps) / -log eps])
@@ -99,6 +116,14 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(const __grid_constant__
   const long long pix = (static_cast<long long>(ph) * a.p + p1) * a.w + static_cast<long long>(pw) * a.p;
   for (int p2 = 0; p2 < a.p; ++p2) {
     float val = __ldg(yrow + f.col + p1 * a.p + p2);
+    if (f.cos_col >= 0) {
+      // rad2deg(atan2(sin, cos)) % 360 with torch's floored remainder (aurora.py:897-904)
+      const float c = __ldg(yrow + f.cos_col + p1 * a.p + p2);
+      float deg = atan2f(val, c) * 57.29577951308232f;
+      float r = fmodf(deg, 360.f);
+      if (r != 0.f && r < 0.f) r += 360.f;
+      val = r;
+    }
     if (f.mod_col >= 0) {
       // pred = model + (1 + mod) * prev   in normalised units (aurora.py:767-775)
       const float mod = __ldg(yrow + f.mod_col + p1 * a.p + p2);
@@ -107,6 +132,13 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(const __grid_constant__
     }
     if (f.clamp_max1) val = fminf(val, 1.f);
     if (f.clamp_min0) val = fmaxf(val, 0.f);
+    if (f.dens_col >= 0) {
+      // density = sigmoid(logit) * wmb_mask; data = value * wmb_mask; data[density < 0.5] = NaN (aurora.py:906-918)
+      const float m = __ldg(f.mask + pix + p2) > f.mask_min ? 1.f : 0.f;
+      const float logit = __ldg(yrow + f.dens_col + p1 * a.p + p2);
+      const float density = m / (1.f + expf(-logit));
+      val = density < 0.5f ? __int_as_float(0x7fc00000) : val * m;
+    }
     f.ptr[pix + p2] = val * f.scale + f.loc;
   }
 }
@@ -158,6 +190,10 @@ extern "C" int ab_unpatchify(const AbFieldOut* fields, int32_t nfields, const fl
     AB_CHECK_ARG(fields[i].ptr != nullptr, "ab_unpatchify: null output plane for field %d", i);
     AB_CHECK_ARG(fields[i].mod_col < 0 || fields[i].prev != nullptr, "ab_unpatchify: modulation needs prev (field %d)", i);
     AB_CHECK_ARG(fields[i].col >= 0 && fields[i].col + p * p <= ldy, "ab_unpatchify: column out of range (field %d)", i);
+    AB_CHECK_ARG(fields[i].cos_col < 0 || fields[i].cos_col + p * p <= ldy,
+                 "ab_unpatchify: cosine column out of range (field %d)", i);
+    AB_CHECK_ARG(fields[i].dens_col < 0 || (fields[i].dens_col + p * p <= ldy && fields[i].mask != nullptr),
+                 "ab_unpatchify: density column out of range or null mask (field %d)", i);
   }
   a.y = y;
   a.nfields = nfields;

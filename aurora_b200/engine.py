@@ -42,6 +42,40 @@ AIR_DIFF_DIM = {"pm1": 0, "pm2p5": 0, "pm10": 0, "co": 1, "tcco": 1, "no": 0, "t
                 "so2": 1, "tcso2": 1, "go3": 1, "gtco3": 1}
 
 
+def wave_channels(names, density_vars, angle_vars):
+    """Names-only replay of `AuroraWave._pre_encoder_hook` (aurora.py:874-892): the hook walks the surface
+    variables in order, APPENDS `<name>_density` / `<name>_sin` / `<name>_cos` to the dict and deletes the
+    angle itself, so the encoder / decoder see [remaining originals in order] + [derived channels in the order
+    they were appended].  Returns [(channel name, source variable, AB_IN_* transform)]."""
+    ch: dict = {n: (n, cabi.AB_IN_PLAIN) for n in names}
+    for n in tuple(names):
+        if n in density_vars and f"{n}_density" not in ch:
+            ch[f"{n}_density"] = (n, cabi.AB_IN_DENSITY)
+            ch[n] = (n, cabi.AB_IN_NAN_TO_ZERO)
+        if n in angle_vars and not (f"{n}_sin" in ch and f"{n}_cos" in ch):
+            ch[f"{n}_sin"] = (n, cabi.AB_IN_SIN_DEG)
+            ch[f"{n}_cos"] = (n, cabi.AB_IN_COS_DEG)
+            del ch[n]
+    return [(k, src, tr) for k, (src, tr) in ch.items()]
+
+
+def wave_outputs(channels, density_vars, angle_vars):
+    """Surface variables of an AuroraWave prediction after `_post_decoder_hook` (aurora.py:894-920), in the
+    reference's dict order: channels that are neither sine / cosine nor density, then the angles in
+    `angle_surf_vars` order.  Returns [(name, value-or-sine channel, cosine channel | None, density channel | None)]."""
+    names = [k for k, _, _ in channels]
+    out: dict = {k: [k, None, None] for k in names}
+    for n in angle_vars:
+        if f"{n}_sin" in out and f"{n}_cos" in out:
+            out[n] = [f"{n}_sin", f"{n}_cos", None]
+            del out[f"{n}_sin"], out[f"{n}_cos"]
+    for n in density_vars:
+        if n in out:
+            out[n][2] = f"{n}_density"
+            del out[f"{n}_density"]
+    return [(k, v[0], v[1], v[2]) for k, v in out.items()]
+
+
 def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
@@ -61,8 +95,9 @@ class AuroraEngine:
     """Runs `Aurora.forward` for one parameter set on one CUDA device."""
 
     def __init__(self, cfg: ModelConfig, params: dict[str, torch.Tensor], variant: str = "base",
-                 edge_dtype: str = "fp16") -> None:
+                 edge_dtype: str = "fp16", variant_args: Optional[dict] = None) -> None:
         self.cfg = cfg
+        self.variant_args = dict(variant_args or {})  # wave: density_vars / angle_vars (aurora.py:816-824)
         self.shard_group = None  # torch.distributed group used by forward(..., sharded=True)
         self.use_cuda_graph = False  # replay the step from a captured CUDA graph (outputs become static buffers)
         self._graphs: dict = {}
@@ -299,6 +334,10 @@ class AuroraEngine:
             return cabi.AB_IN_CLAMP_MIN0, None
         return cabi.AB_IN_PLAIN, None
 
+    def _wave_channels(self, surf_names):
+        va = self.variant_args
+        return wave_channels(tuple(surf_names), va["density_vars"], va["angle_vars"])
+
     def _dynamic_values(self, tm) -> list[float]:
         return [
             float(np.cos(2 * np.pi * tm.hour / 24)), float(np.sin(2 * np.pi * tm.hour / 24)),
@@ -335,12 +374,19 @@ class AuroraEngine:
         static_names = tuple(batch.static_vars)
         atmos_names = tuple(batch.atmos_vars)
         fields_s, names_s = [], []
-        for k in surf_names:
-            loc, sc = surf_stats_of(k, surf_stats)
-            tr, comb = self._surf_transform(k)
-            v = batch.surf_vars[k]
-            fields_s.append(self._field_in(v[b], h * w, loc, sc, tr, comb))
-            names_s.append(k)
+        if self.variant == "wave":
+            # density / sine / cosine channels are formed from the normalised value while loading (aurora.py:874-892)
+            for ch, src, tr in self._wave_channels(surf_names):
+                loc, sc = surf_stats_of(src, surf_stats)
+                fields_s.append(self._field_in(batch.surf_vars[src][b], h * w, loc, sc, tr))
+                names_s.append(ch)
+        else:
+            for k in surf_names:
+                loc, sc = surf_stats_of(k, surf_stats)
+                tr, comb = self._surf_transform(k)
+                v = batch.surf_vars[k]
+                fields_s.append(self._field_in(v[b], h * w, loc, sc, tr, comb))
+                names_s.append(k)
         static_fields = []
         for k in static_names:
             loc, sc = surf_stats_of(k, surf_stats)
@@ -614,12 +660,33 @@ class AuroraEngine:
 
         # ---- surface heads on latent level 0 (decoder.py:214-217) ----
         surf_in = tuple(batch.surf_vars)
+        wave = self.variant == "wave"
+        if wave:
+            chans = self._wave_channels(surf_in)
+            surf_in = tuple(k for k, _, _ in chans)
         surf_names = surf_in + tuple(f"{n}_mod" for n in surf_in if n in cfg.modulation_heads)
         w_s, b_s = self._head_weight("surf_heads", surf_names)
         ys = self._buffer("dec.ys", (l, len(surf_names) * pp), torch.float32)
         cabi.gemm(xdec[:l], w_s, bias=b_s, out_f32=ys)
         fo = []
-        for k in (surf_in if air else surf_names):
+        if wave:
+            # angles back from (sin, cos), density channels -> NaN mask on the wave-model mask (aurora.py:894-920)
+            va = self.variant_args
+            wmb = batch.static_vars["wmb"]
+            wmb_loc, _ = surf_stats_of("wmb", surf_stats)
+            for k, val_ch, cos_ch, dens_ch in wave_outputs(chans, va["density_vars"], va["angle_vars"]):
+                loc, sc = surf_stats_of(k, surf_stats)
+                f = cabi.AbFieldOut()
+                f.ptr = out_surf[k][b, 0].data_ptr()
+                f.loc, f.scale = loc, sc
+                f.col = surf_names.index(val_ch) * pp
+                if cos_ch is not None:
+                    f.cos_col = surf_names.index(cos_ch) * pp
+                if dens_ch is not None:
+                    f.dens_col = surf_names.index(dens_ch) * pp
+                    f.mask, f.mask_min = wmb.data_ptr(), wmb_loc
+                fo.append(f)
+        for k in (() if wave else surf_in if air else surf_names):
             loc, sc = surf_stats_of(k, surf_stats)
             f = cabi.AbFieldOut()
             f.ptr = out_surf[k][b, 0].data_ptr()
@@ -761,6 +828,10 @@ class AuroraEngine:
         air = self.variant == "air_pollution"
         surf_out_names = tuple(batch.surf_vars) if air else tuple(batch.surf_vars) + tuple(
             f"{n}_mod" for n in batch.surf_vars if n in cfg.modulation_heads)
+        if self.variant == "wave":
+            va = self.variant_args
+            surf_out_names = tuple(k for k, *_ in wave_outputs(
+                self._wave_channels(tuple(batch.surf_vars)), va["density_vars"], va["angle_vars"]))
         atmos_out_names = tuple(batch.atmos_vars) if air else tuple(batch.atmos_vars) + tuple(
             f"{n}_mod" for n in batch.atmos_vars if n in cfg.modulation_heads)
         out_surf = {k: torch.empty(bsz, 1, h, w, dtype=torch.float32, device=self.device) for k in surf_out_names}

@@ -22,7 +22,7 @@ from aurora_b200.spec import ModelConfig, init_state_dict, param_specs
 
 __all__ = [
     "Aurora", "AuroraPretrained", "AuroraSmallPretrained", "AuroraSmall", "Aurora12hPretrained", "AuroraHighRes",
-    "AuroraAirPollution",
+    "AuroraAirPollution", "AuroraWave",
 ]
 
 
@@ -100,6 +100,9 @@ class Aurora(nn.Module):
     def _extra_specs(self):
         return ()
 
+    def _variant_args(self) -> dict:
+        return {}
+
     def _put(self, key: str, value: torch.Tensor) -> None:
         path = key.split(".")
         if path[0] not in self._modules:
@@ -118,7 +121,8 @@ class Aurora(nn.Module):
                 raise NotImplementedError(
                     f"aurora_b200 keeps fp32 master parameters and computes with bf16 operands / fp32 accumulation; "
                     f"parameters of dtype {p0.dtype} are not supported")
-            self._engine = AuroraEngine(self.config, {k: v.data for k, v in params.items()}, variant=self._variant)
+            self._engine = AuroraEngine(self.config, {k: v.data for k, v in params.items()}, variant=self._variant,
+                                        variant_args=self._variant_args())
             self._engine_sig = sig
         self._engine.use_cuda_graph = bool(self.use_cuda_graph)
         return self._engine
@@ -163,9 +167,11 @@ class Aurora(nn.Module):
         self.load_state_dict(d, strict=strict)
 
     def _adapt_checkpoint(self, d: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
-        """Key renaming of the published checkpoint files (`aurora/model/compat.py`) is host-side loader
-        logic outside the accelerated path; checkpoints already in the current key layout load as is."""
-        return d
+        """Bring a published checkpoint file to the current key layout (`aurora.py:458-467`,
+        `aurora/model/compat.py:19-78`); a no-op for checkpoints already in that layout."""
+        from aurora_b200 import compat
+
+        return compat.adapt_pretrained(self.patch_size, d)
 
     def adapt_checkpoint_max_history_size(self, checkpoint: dict[str, torch.Tensor]) -> None:
         """Zero-extend the history dimension of the patch-embedding weights (`aurora.py:469-504`)."""
@@ -265,3 +271,70 @@ class AuroraAirPollution(Aurora):
                 out.append((f"{grp}.{v}.weight", (1, 2), "half"))
                 out.append((f"{grp}.{v}.bias", (1,), "zeros"))
         return out
+
+    def _adapt_checkpoint(self, d: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
+        from aurora_b200 import compat
+
+        return compat.adapt_air_pollution(self.patch_size, Aurora._adapt_checkpoint(self, d))
+
+
+_WAVE_VARS = (("swh", "mwd", "mwp", "pp1d", "shww", "mdww", "mpww", "shts", "mdts", "mpts")
+              + ("swh1", "mwd1", "mwp1", "swh2", "mwd2", "mwp2", "wind", "10u_wave", "10v_wave"))
+
+
+class AuroraWave(Aurora):
+    """HRES-WAM ocean-wave fine-tune (aurora.py:804-920).  Wave variables that are absent are NaN in the data:
+    every such variable gets a `<name>_density` presence channel, directions are modelled as sine / cosine.
+    The channel construction runs inside the patch loader, the inverse (atan2, density -> NaN on the wave
+    model mask `wmb`) inside the un-patchify kernel (`csrc/patch_io.cu`)."""
+
+    default_checkpoint_name = "aurora-0.25-wave.ckpt"
+    default_checkpoint_revision = "74598e8c65d53a96077c08bb91acdfa5525340c9"
+    _variant = "wave"
+
+    def __init__(
+        self, *,
+        surf_vars=("2t", "10u", "10v", "msl") + _WAVE_VARS,
+        static_vars=("lsm", "z", "slt", "wmb", "lat_mask"),
+        lora_mode: str = "from_second", stabilise_level_agg: bool = True,
+        density_channel_surf_vars=_WAVE_VARS,
+        angle_surf_vars=("mwd", "mdww", "mdts", "mwd1", "mwd2"), **kw,
+    ) -> None:
+        # the network models the sine, cosine and density versions of the variables (aurora.py:826-834)
+        supplemented: tuple[str, ...] = ()
+        for name in surf_vars:
+            supplemented += (f"{name}_sin", f"{name}_cos") if name in angle_surf_vars else (name,)
+            if name in density_channel_surf_vars:
+                supplemented += (f"{name}_density",)
+        super().__init__(surf_vars=supplemented, static_vars=static_vars, lora_mode=lora_mode,
+                         stabilise_level_agg=stabilise_level_agg, **kw)
+        self.density_channel_surf_vars = tuple(density_channel_surf_vars)
+        self.angle_surf_vars = tuple(angle_surf_vars)
+
+    def _variant_args(self) -> dict:
+        return {"density_vars": self.density_channel_surf_vars, "angle_vars": self.angle_surf_vars}
+
+    def _adapt_checkpoint(self, d: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
+        from aurora_b200 import compat
+
+        return compat.adapt_wave(self.patch_size, Aurora._adapt_checkpoint(self, d))
+
+    def batch_transform_hook(self, batch: Batch) -> Batch:
+        """Host-side preparation of raw HRES-WAM fields, before normalisation (aurora.py:851-890): wind speed +
+        direction -> components, and at the first step waves of (practically) zero height are marked absent."""
+        surf = dict(batch.surf_vars)
+        if "dwi" in surf and "wind" in surf:
+            ang = torch.deg2rad(surf.pop("dwi"))
+            surf["10u_wave"] = -surf["wind"] * torch.sin(ang)
+            surf["10v_wave"] = -surf["wind"] * torch.cos(ang)
+        if batch.metadata.rollout_step == 0:
+            families = (("swh", ("mwd", "mwp", "pp1d")), ("shww", ("mdww", "mpww")), ("shts", ("mdts", "mdts")),
+                        ("swh1", ("mwd1", "mwp1")), ("swh2", ("mwd2", "mwp2")))
+            for height, others in families:
+                absent = surf[height] < 1e-4
+                if bool(absent.any()):
+                    for name in (height,) + others:
+                        surf[name] = surf[name].masked_fill(absent, float("nan"))
+                        if name not in self.angle_surf_vars:
+                            assert int((surf[name] < 1e-4).sum()) == 0
+        return dataclasses.replace(batch, surf_vars=surf)

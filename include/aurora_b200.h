@@ -204,16 +204,26 @@ int ab_linear_small_f32(const float* x, const float* w, const float* bias, float
 /* ------------------------------------------------------------------------------------------------
  * Batch <-> token matrix.  Field descriptors are HOST arrays (copied into the launch).
  * ---------------------------------------------------------------------------------------------- */
-#define AB_MAX_FIELDS 40
+#define AB_MAX_FIELDS 64
 
-enum { AB_IN_PLAIN = 0, AB_IN_CLAMP_MIN0 = 1, AB_IN_CLAMP_LOG_COMBINE = 2 };
+enum {
+  AB_IN_PLAIN = 0,
+  AB_IN_CLAMP_MIN0 = 1,
+  AB_IN_CLAMP_LOG_COMBINE = 2,
+  /* AuroraWave._pre_encoder_hook (aurora.py:874-892), applied to the NORMALISED value z: */
+  AB_IN_NAN_TO_ZERO = 3, /* z.nan_to_num(0)                              (value channel of a density variable) */
+  AB_IN_DENSITY = 4,     /* (~isnan(z)).float()                          (`<name>_density`) */
+  AB_IN_SIN_DEG = 5,     /* sin(deg2rad(z)).nan_to_num(0)                (`<name>_sin`) */
+  AB_IN_COS_DEG = 6      /* cos(deg2rad(z)).nan_to_num(0)                (`<name>_cos`) */
+};
 
 typedef struct AbFieldIn {
   const float* ptr;   /* (T, H, W) planes of one variable (one batch element, one level); NULL = constant */
   int64_t stride_t;   /* elements between history steps (0 for static variables) */
   float loc, scale;   /* normalisation (x - loc) / scale   (batch.py:94-116, normalisation.py:34-70) */
   float const_value;  /* normalised value when ptr == NULL (dynamic time-of-day style variables) */
-  int32_t transform;  /* AB_IN_* : positive clamp (aurora.py:302-317) / AirPollution combiner (:733-742) */
+  int32_t transform;  /* AB_IN_* : positive clamp (aurora.py:302-317) / AirPollution combiner (:733-742) /
+                         AuroraWave density + angle channels (:874-892) */
   float w0, w1, wb;   /* combiner Linear(2,1) weights and bias */
 } AbFieldIn;
 
@@ -231,6 +241,11 @@ typedef struct AbFieldOut {
   int32_t mod_col;    /* first column of its modulation head (aurora.py:767-775) or -1 */
   int32_t clamp_min0; /* positive-variable clamp (aurora.py:367-388) */
   int32_t clamp_max1; /* AirPollution SO2 >= 850 hPa clamp (aurora.py:787-794) */
+  /* AuroraWave._post_decoder_hook (aurora.py:894-920); all in normalised units, before y * scale + loc: */
+  int32_t cos_col;    /* >= 0: `col` holds the sine head, this the cosine head; value = rad2deg(atan2(s, c)) mod 360 */
+  int32_t dens_col;   /* >= 0: density-logit head; value *= m, NaN where sigmoid(logit) * m < 0.5, m = mask > mask_min */
+  const float* mask;  /* (H, W) plane of the `wmb` static variable, physical units; needed when dens_col >= 0 */
+  float mask_min;     /* physical-unit threshold equivalent to "normalised wmb > 0" (= its location) */
 } AbFieldOut;
 
 /* y f32 [ (H/p)*(W/p), ldy ] (head GEMM output, column col + p1*p + p2) -> planes.  Replaces torch.stack +

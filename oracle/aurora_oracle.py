@@ -6,7 +6,8 @@ reference arm may import it.  The product (`aurora_b200/`) never does and has no
 It is a from-scratch functional restatement (no nn.Module, explicit gather maps instead of
 roll/pad/partition copies, patch embedding as a GEMM) of:
 
-* Aurora.forward                      aurora/model/aurora.py:265-392 (+ AirPollution hooks :726-796)
+* Aurora.forward                      aurora/model/aurora.py:265-392 (+ AirPollution hooks :726-796,
+                                      AuroraWave hooks :851-920)
 * Perceiver3DEncoder.forward          aurora/model/encoder.py:198-366
 * LevelPatchEmbed.forward             aurora/model/patchembed.py:79-118
 * PerceiverResampler / Attention      aurora/model/perceiver.py:127-152, 212-233
@@ -479,13 +480,69 @@ def _combine(sd, group, name, z):
     return F.linear(feats, wgt, bias)[..., 0]
 
 
+def wave_batch_transform(batch: Batch, angle_vars) -> Batch:
+    """AuroraWave.batch_transform_hook (aurora.py:851-890): wind speed / direction -> components; at roll-out
+    step 0 a wave family whose height is < 1e-4 is marked absent (NaN)."""
+    surf = dict(batch.surf_vars)
+    if "dwi" in surf and "wind" in surf:
+        surf["10u_wave"] = -surf["wind"] * torch.sin(torch.deg2rad(surf["dwi"]))
+        surf["10v_wave"] = -surf["wind"] * torch.cos(torch.deg2rad(surf["dwi"]))
+        del surf["dwi"]
+    if batch.metadata.rollout_step == 0:
+        for height, others in (("swh", ("mwd", "mwp", "pp1d")), ("shww", ("mdww", "mpww")),
+                               ("shts", ("mdts", "mdts")), ("swh1", ("mwd1", "mwp1")), ("swh2", ("mwd2", "mwp2"))):
+            absent = surf[height] < 1e-4
+            if absent.sum() > 0:
+                for name in (height,) + others:
+                    x = surf[name].clone()
+                    x[absent] = float("nan")
+                    surf[name] = x
+    return dataclasses.replace(batch, surf_vars=surf)
+
+
+def _wave_pre(surf: dict, density_vars, angle_vars) -> dict:
+    """AuroraWave._pre_encoder_hook (aurora.py:874-892) on normalised fields: new channels are appended to the
+    dict in the order the loop meets them, the angle itself is removed."""
+    surf = dict(surf)
+    for name in list(surf):
+        x = surf[name]
+        if name in density_vars and f"{name}_density" not in surf:
+            surf[f"{name}_density"] = (~torch.isnan(x)).to(x.dtype)
+            surf[name] = x.nan_to_num(0)
+        if name in angle_vars and not (f"{name}_sin" in surf and f"{name}_cos" in surf):
+            surf[f"{name}_sin"] = torch.sin(torch.deg2rad(x)).nan_to_num(0)
+            surf[f"{name}_cos"] = torch.cos(torch.deg2rad(x)).nan_to_num(0)
+            del surf[name]
+    return surf
+
+
+def _wave_post(pred_surf: dict, wmb: Tensor, density_vars, angle_vars) -> dict:
+    """AuroraWave._post_decoder_hook (aurora.py:894-920), normalised units; `wmb` is the normalised mask."""
+    out = dict(pred_surf)
+    mask = wmb > 0
+    for name in angle_vars:
+        if f"{name}_sin" in out and f"{name}_cos" in out:
+            out[name] = torch.rad2deg(torch.atan2(out.pop(f"{name}_sin"), out.pop(f"{name}_cos"))) % 360
+    for name in density_vars:
+        if name in out:
+            density = torch.sigmoid(out.pop(f"{name}_density")) * mask
+            data = out[name] * mask
+            data[density < 0.5] = float("nan")
+            out[name] = data
+    return out
+
+
 # -------------------------------------------------------------------------------------------------
 # whole model
 # -------------------------------------------------------------------------------------------------
 def forward(cfg: ModelConfig, sd: dict[str, Tensor], batch: Batch, dtype=torch.float32, taps: Optional[dict] = None,
-            variant: str = "base") -> Batch:
+            variant: str = "base", variant_args: Optional[dict] = None) -> Batch:
     """`Aurora.forward` (aurora.py:265-392) on the CPU.  `variant="air_pollution"` adds the
-    AuroraAirPollution pre/post hooks."""
+    AuroraAirPollution pre/post hooks, `variant="wave"` the AuroraWave ones (`variant_args` =
+    {"density_vars": ..., "angle_vars": ...})."""
+    va = variant_args or {}
+    if variant == "wave":
+        batch = wave_batch_transform(batch, va["angle_vars"])
     sd = {k: v.to(dtype) for k, v in sd.items()}
     surf_stats = dict(cfg.surf_stats) if cfg.surf_stats else None
     batch = batch.type(dtype)
@@ -507,6 +564,12 @@ def forward(cfg: ModelConfig, sd: dict[str, Tensor], batch: Batch, dtype=torch.f
             surf_vars={k: _combine(sd, "surf_feature_combiner", k, v) if k in cfg.positive_surf_vars else v for k, v in tb.surf_vars.items()},
             atmos_vars={k: _combine(sd, "atmos_feature_combiner", k, v) if k in cfg.positive_atmos_vars else v for k, v in tb.atmos_vars.items()},
         )
+    if variant == "wave":
+        # The reference's hook MUTATES the surf_vars dict that `batch` and the transformed batch share (no
+        # positive variables => same object, aurora.py:299-320), so the decoder sees the derived channels too.
+        assert not cfg.positive_surf_vars
+        tb = dataclasses.replace(tb, surf_vars=_wave_pre(tb.surf_vars, va["density_vars"], va["angle_vars"]))
+        batch = dataclasses.replace(batch, surf_vars=tb.surf_vars)
     x = encoder_forward(sd, cfg, tb, taps)
     if taps is not None:
         taps["encoder"] = x
@@ -536,6 +599,9 @@ def forward(cfg: ModelConfig, sd: dict[str, Tensor], batch: Batch, dtype=torch.f
                 sec = pred.atmos_vars["so2"][..., i, :, :]
                 parts.append(sec.clamp(max=1) if lv >= 850 else sec)
             pred.atmos_vars["so2"] = torch.stack(parts, dim=-3)
+    if variant == "wave":
+        pred = dataclasses.replace(pred, surf_vars=_wave_post(
+            pred.surf_vars, pred.static_vars["wmb"], va["density_vars"], va["angle_vars"]))
     step = pred.metadata.rollout_step
     clamp_now = step >= 1 if cfg.clamp_at_first_step else step > 1
     if cfg.positive_surf_vars and clamp_now:
@@ -545,11 +611,13 @@ def forward(cfg: ModelConfig, sd: dict[str, Tensor], batch: Batch, dtype=torch.f
     return pred.unnormalise(surf_stats=surf_stats)
 
 
-def rollout(cfg: ModelConfig, sd, batch: Batch, steps: int, dtype=torch.float32, variant="base"):
+def rollout(cfg: ModelConfig, sd, batch: Batch, steps: int, dtype=torch.float32, variant="base", variant_args=None):
     """Autoregressive roll-out generator (rollout.py:14-49)."""
+    if variant == "wave":
+        batch = wave_batch_transform(batch, variant_args["angle_vars"])
     batch = batch.type(dtype).crop(cfg.patch_size).to("cpu")
     for _ in range(steps):
-        pred = forward(cfg, sd, batch, dtype=dtype, variant=variant)
+        pred = forward(cfg, sd, batch, dtype=dtype, variant=variant, variant_args=variant_args)
         yield pred
         batch = dataclasses.replace(
             pred,

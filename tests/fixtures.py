@@ -28,6 +28,25 @@ AIR_STATIC = ("lsm", "z", "slt", "static_ammonia", "static_ammonia_log", "static
 AIR_ATMOS = ("z", "u", "v", "t", "q", "co", "no", "no2", "go3", "so2")
 AIR_DIFF = ("pm1", "pm2p5", "pm10", "co", "tcco", "no", "tc_no", "no2", "tcno2", "so2", "tcso2", "go3", "gtco3")
 
+# AuroraWave (aurora.py:804-849): raw HRES-WAM variable names and the channels the network models
+WAVE_VARS = (("swh", "mwd", "mwp", "pp1d", "shww", "mdww", "mpww", "shts", "mdts", "mpts")
+             + ("swh1", "mwd1", "mwp1", "swh2", "mwd2", "mwp2", "wind", "10u_wave", "10v_wave"))
+WAVE_RAW_SURF = ("2t", "10u", "10v", "msl") + WAVE_VARS
+WAVE_ANGLES = ("mwd", "mdww", "mdts", "mwd1", "mwd2")
+WAVE_HEIGHTS = ("swh", "shww", "shts", "swh1", "swh2")
+WAVE_STATIC = ("lsm", "z", "slt", "wmb", "lat_mask")
+WAVE_ARGS = {"density_vars": WAVE_VARS, "angle_vars": WAVE_ANGLES}
+
+
+def wave_supplemented(raw=WAVE_RAW_SURF) -> tuple[str, ...]:
+    out: tuple[str, ...] = ()
+    for name in raw:
+        out += (f"{name}_sin", f"{name}_cos") if name in WAVE_ANGLES else (name,)
+        if name in WAVE_VARS:
+            out += (f"{name}_density",)
+    return out
+
+
 CONFIGS: dict[str, ModelConfig] = {
     # 3-stage U-Net, head_dim 64 in every Swin stage like all presets; tiny widths.
     "tiny": ModelConfig(
@@ -52,6 +71,11 @@ CONFIGS: dict[str, ModelConfig] = {
         timestep=timedelta(hours=12), level_condition=LEVELS13, dynamic_vars=True, atmos_static_vars=True,
         separate_perceiver=("co", "no", "no2", "go3", "so2"), modulation_heads=AIR_DIFF,
         positive_surf_vars=AIR_SURF[4:], positive_atmos_vars=AIR_ATMOS[5:], simulate_indexing_bug=True,
+        embed_dim=128, num_heads=4, encoder_depths=(2, 2, 2), encoder_num_heads=(2, 4, 8),
+        decoder_depths=(2, 2, 2), decoder_num_heads=(8, 4, 2), use_lora=True,
+    ),
+    "tiny_wave": ModelConfig(
+        surf_vars=wave_supplemented(), static_vars=WAVE_STATIC, lora_mode="from_second", stabilise_level_agg=True,
         embed_dim=128, num_heads=4, encoder_depths=(2, 2, 2), encoder_num_heads=(2, 4, 8),
         decoder_depths=(2, 2, 2), decoder_num_heads=(8, 4, 2), use_lora=True,
     ),
@@ -144,6 +168,43 @@ def make_batch(cfg: ModelConfig, h: int, w: int, levels=LEVELS13, b: int = 1, t:
     return Batch(surf, static, atmos, meta)
 
 
+def make_wave_batch(cfg: ModelConfig, h: int, w: int, levels=LEVELS4, seed: int = 0, rollout_step: int = 0,
+                    with_dwi: bool = True) -> Batch:
+    """HRES-WAM-shaped synthetic batch for AuroraWave: ERA5 part from `make_batch`, wave heights / periods
+    positive, directions uniform in [0, 360), NaN over "land" (absent waves), a patch of (practically) zero wave
+    height (absent at step 0 via `batch_transform_hook`), 0/1 `wmb` / `lat_mask` static masks, and wind as speed +
+    direction (`dwi`) so that the component split of the hook is exercised."""
+    era = dataclasses.replace(cfg, surf_vars=("2t", "10u", "10v", "msl"), static_vars=("lsm", "z", "slt"))
+    base = make_batch(era, h, w, levels=levels, b=1, seed=seed, rollout_step=rollout_step)
+    rng = np.random.Generator(np.random.PCG64(5000 + seed))
+    t = 2
+    yy, xx = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    land = ((yy // 5 + xx // 7) % 4 == 0)  # blocks of NaN
+    calm = ((yy // 4 + 2 * (xx // 6)) % 7 == 0) & ~land  # blocks of zero wave height
+    surf = dict(base.surf_vars)
+    for k in WAVE_VARS:
+        if with_dwi and k in ("10u_wave", "10v_wave"):
+            continue
+        loc, sc = surf_stats_of(k)
+        if k in WAVE_ANGLES:
+            a = rng.uniform(0.0, 360.0, (1, t, h, w))
+        elif k in ("10u_wave", "10v_wave"):
+            a = loc + sc * rng.standard_normal((1, t, h, w))
+        else:
+            a = np.maximum(np.abs(loc + sc * rng.standard_normal((1, t, h, w))), 0.05)
+        if k != "wind":
+            a = np.where(land[None, None], np.nan, a)
+        if k in WAVE_HEIGHTS:
+            a = np.where(calm[None, None], 0.0, a)
+        surf[k] = torch.from_numpy(a.astype(np.float32))
+    if with_dwi:
+        surf["dwi"] = torch.from_numpy(rng.uniform(0.0, 360.0, (1, t, h, w)).astype(np.float32))
+    static = dict(base.static_vars)
+    static["wmb"] = torch.from_numpy((~((yy // 6 + xx // 5) % 5 == 0)).astype(np.float32))
+    static["lat_mask"] = torch.from_numpy((np.abs(yy - h / 2) < 0.45 * h).astype(np.float32))
+    return Batch(surf, static, base.atmos_vars, base.metadata)
+
+
 def reference_kwargs(cfg: ModelConfig) -> dict:
     """Constructor keyword arguments for the reference's `Aurora(...)` equivalent to `cfg`."""
     kw = dataclasses.asdict(cfg)
@@ -154,3 +215,40 @@ def reference_kwargs(cfg: ModelConfig) -> dict:
 def rel_mean_abs(out: torch.Tensor, ref: torch.Tensor) -> float:
     """The reference's own acceptance metric: mean|out - ref| / mean|ref| (tests/test_model.py:45-61)."""
     return float((out.double() - ref.double()).abs().mean() / ref.double().abs().mean().clamp_min(1e-30))
+
+
+def field_error(out: torch.Tensor, ref: torch.Tensor, angle: bool = False) -> tuple[float, float]:
+    """(rel-mean-abs over the points finite on both sides, fraction of points whose NaN-ness differs).
+    For fields without NaN this is `rel_mean_abs`; wave-model outputs carry NaN where a wave component is absent
+    (aurora.py:906-918).  `angle=True` measures the circular difference of directions in degrees."""
+    out, ref = out.double(), ref.double()
+    nan_o, nan_r = torch.isnan(out), torch.isnan(ref)
+    mismatch = float((nan_o != nan_r).double().mean())
+    both = ~nan_o & ~nan_r
+    if not bool(both.any()):
+        return 0.0, mismatch
+    diff = out[both] - ref[both]
+    if angle:
+        diff = torch.remainder(diff + 180.0, 360.0) - 180.0
+    return float(diff.abs().mean() / ref[both].abs().mean().clamp_min(1e-30)), mismatch
+
+
+def case_inputs(case: tuple):
+    """(cfg, state dict, batch, oracle variant, variant args, extra param specs) of a tests/golden/cases.py entry."""
+    cfg_name, cls_name, h, w, levels, bsz, step, seed = case
+    cfg = CONFIGS[cfg_name]
+    extra = air_extra_specs(cfg) if cls_name == "AuroraAirPollution" else ()
+    sd = make_state_dict(cfg, seed=seed, extra=extra)
+    if cls_name == "AuroraWave":
+        batch = make_wave_batch(cfg, h, w, levels=levels, seed=seed, rollout_step=step, with_dwi=step == 0)
+        return cfg, sd, batch, "wave", WAVE_ARGS, extra
+    batch = make_batch(cfg, h, w, levels=levels, b=bsz, seed=seed, rollout_step=step)
+    return cfg, sd, batch, ("air_pollution" if cls_name == "AuroraAirPollution" else "base"), None, extra
+
+
+def model_kwargs(cfg: ModelConfig, cls_name: str) -> dict:
+    """Constructor arguments of the model class `cls_name` (reference or ours) equivalent to `cfg`."""
+    kw = reference_kwargs(cfg)
+    if cls_name == "AuroraWave":  # the class derives the modelled channels from the raw variable names itself
+        kw["surf_vars"] = WAVE_RAW_SURF
+    return kw

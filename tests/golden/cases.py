@@ -12,5 +12,7 @@ MODEL_CASES = {
     "tiny_12h_stab_step1": ("tiny_12h_stab", "Aurora", 17, 32, fx.LEVELS4, 1, 1, 4),
     "tiny_air_46x90": ("tiny_air", "AuroraAirPollution", 46, 90, fx.LEVELS13, 1, 0, 5),
     "tiny_air_46x90_step2": ("tiny_air", "AuroraAirPollution", 46, 90, fx.LEVELS13, 1, 2, 5),
+    "tiny_wave_33x64": ("tiny_wave", "AuroraWave", 33, 64, fx.LEVELS4, 1, 0, 8),
+    "tiny_wave_33x64_step1": ("tiny_wave", "AuroraWave", 33, 64, fx.LEVELS4, 1, 1, 8),
     "small_17x32": ("small", "AuroraSmallPretrained", 17, 32, fx.LEVELS4, 1, 0, 6),
 }

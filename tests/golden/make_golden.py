@@ -15,6 +15,7 @@ import dataclasses
 import hashlib
 import json
 import sys
+import types
 from pathlib import Path
 
 import numpy as np
@@ -90,8 +91,7 @@ from tests.golden.cases import MODEL_CASES  # noqa: E402
 def build_reference(cfg_name, cls_name, seed):
     cfg = fx.CONFIGS[cfg_name]
     cls = getattr(aurora, cls_name)
-    kw = fx.reference_kwargs(cfg)
-    model = cls(**kw)
+    model = cls(**fx.model_kwargs(cfg, cls_name))
     extra = fx.air_extra_specs(cfg) if cls_name == "AuroraAirPollution" else ()
     sd = fx.make_state_dict(cfg, seed=seed, extra=extra)
     model.load_state_dict(sd, strict=True)  # also proves key/shape parity of aurora_b200.spec
@@ -107,10 +107,12 @@ def to_ref_batch(b):
     )
 
 
-def gen_models():
+def gen_models(only=None):
     for name, (cfg_name, cls_name, h, w, levels, bsz, step, seed) in MODEL_CASES.items():
+        if only and not any(name.startswith(o) for o in only):
+            continue
         cfg, model, _ = build_reference(cfg_name, cls_name, seed)
-        batch = fx.make_batch(cfg, h, w, levels=levels, b=bsz, seed=seed, rollout_step=step)
+        batch = fx.case_inputs(MODEL_CASES[name])[2]
         taps = {}
         h1 = model.encoder.register_forward_hook(lambda m, i, o: taps.__setitem__("encoder", o.detach()))
         h2 = model.backbone.register_forward_hook(lambda m, i, o: taps.__setitem__("backbone", o.detach()))
@@ -146,21 +148,38 @@ def gen_rollout():
 def gen_keys():
     keys = {}
     for cls_name in ("Aurora", "AuroraPretrained", "AuroraSmallPretrained", "Aurora12hPretrained", "AuroraHighRes",
-                     "AuroraAirPollution"):
+                     "AuroraAirPollution", "AuroraWave"):
         m = getattr(aurora, cls_name)()
         keys[cls_name] = {k: list(v.shape) for k, v in m.state_dict().items()}
     (HERE / "keys.json").write_text(json.dumps(keys))
     print("keys.json", {k: len(v) for k, v in keys.items()})
 
 
+def gen_compat():
+    """Published-layout checkpoints through the reference's `_adapt_checkpoint` of each model family."""
+    from tests import compat_fixtures as cf
+
+    out = {}
+    for kind, cls_name in (("pretrained", "AuroraSmallPretrained"), ("air_pollution", "AuroraAirPollution"),
+                           ("wave", "AuroraWave")):
+        holder = types.SimpleNamespace(patch_size=cf.PATCH[kind])  # the adapters only read `self.patch_size`
+        adapted = getattr(aurora, cls_name)._adapt_checkpoint(holder, cf.old_checkpoint(kind))
+        out[kind] = cf.digest(adapted)
+    (HERE / "compat.json").write_text(json.dumps(out, indent=0))
+    print("compat.json", {k: len(v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["windows", "models", "rollout", "keys"]
+    only = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--only=")]  # model case name prefixes
+    what = [a for a in sys.argv[1:] if not a.startswith("--only=")] or ["windows", "models", "rollout", "keys", "compat"]
     torch.manual_seed(0)
     if "windows" in what:
         gen_windows()
     if "models" in what:
-        gen_models()
+        gen_models(only)
     if "rollout" in what:
         gen_rollout()
     if "keys" in what:
         gen_keys()
+    if "compat" in what:
+        gen_compat()

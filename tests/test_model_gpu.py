@@ -19,6 +19,7 @@ from tests.golden.cases import MODEL_CASES
 pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).parent / "golden"
 TOL = 5e-3
+NAN_TOL = 5e-3
 
 CLASS_OF = {"Aurora": "Aurora", "AuroraAirPollution": "AuroraAirPollution", "AuroraSmallPretrained": "AuroraSmallPretrained"}
 
@@ -27,8 +28,7 @@ def _build(cfg_name, cls_name, seed):
     import aurora_b200 as ab
 
     cfg = fx.CONFIGS[cfg_name]
-    kw = fx.reference_kwargs(cfg)
-    model = getattr(ab, cls_name)(**kw)
+    model = getattr(ab, cls_name)(**fx.model_kwargs(cfg, cls_name))
     assert model.config == cfg
     extra = fx.air_extra_specs(cfg) if cls_name == "AuroraAirPollution" else ()
     model.load_state_dict(fx.make_state_dict(cfg, seed=seed, extra=extra), strict=True)
@@ -39,7 +39,8 @@ def _build(cfg_name, cls_name, seed):
 def test_forward_matches_reference_golden(name):
     cfg_name, cls_name, h, w, levels, bsz, step, seed = MODEL_CASES[name]
     cfg, model = _build(cfg_name, cls_name, seed)
-    batch = fx.make_batch(cfg, h, w, levels=levels, b=bsz, seed=seed, rollout_step=step)
+    batch = fx.case_inputs(MODEL_CASES[name])[2]
+    wave = cls_name == "AuroraWave"
     pred = model.forward(batch)
     torch.cuda.synchronize()
     gold = np.load(GOLD / f"model_{name}.npz")
@@ -47,16 +48,22 @@ def test_forward_matches_reference_golden(name):
     assert pred.metadata.time[0].timestamp() == float(gold["meta.time0"])
     worst = 0.0
     for grp, d in (("surf", pred.surf_vars), ("atmos", pred.atmos_vars)):
-        keys = sorted(k[len(grp) + 1:] for k in gold.files if k.startswith(grp + "."))
-        assert keys == sorted(d.keys())
+        keys = [k[len(grp) + 1:] for k in gold.files if k.startswith(grp + ".")]
+        assert sorted(keys) == sorted(d.keys())
+        if wave:
+            assert list(d.keys()) == keys  # dict order produced by the reference's hooks
         for k in keys:
             ref = torch.from_numpy(gold[f"{grp}.{k}"])
             out = d[k].cpu()
             assert out.shape == ref.shape and out.is_floating_point()
-            assert torch.isfinite(out).all(), (grp, k)
-            err = fx.rel_mean_abs(out, ref)
+            if not wave:
+                assert torch.isfinite(out).all(), (grp, k)
+            # wave model: NaN marks an absent wave component (density head < 0.5); a logit within bf16 noise of 0
+            # may flip, so the NaN masks must agree on all but NAN_TOL of the points; directions are compared
+            # on the circle
+            err, nan_mismatch = fx.field_error(out, ref, angle=wave and k in fx.WAVE_ANGLES)
             worst = max(worst, err)
-            assert err < TOL, (name, grp, k, err)
+            assert err < TOL and nan_mismatch < NAN_TOL, (name, grp, k, err, nan_mismatch)
     print(f"[parity] {name}: worst rel-mean-abs {worst:.3e}")
     for k, v in pred.static_vars.items():
         assert torch.equal(v.cpu(), batch.crop(cfg.patch_size).static_vars[k])
@@ -88,6 +95,26 @@ def test_rollout_matches_reference_golden():
             assert fx.rel_mean_abs(v.cpu(), torch.from_numpy(gold[f"step{i}.surf.{k}"])) < TOL * (i + 1), (i, k)
         for k, v in pred.atmos_vars.items():
             assert fx.rel_mean_abs(v.cpu(), torch.from_numpy(gold[f"step{i}.atmos.{k}"])) < TOL * (i + 1), (i, k)
+
+
+def test_wave_rollout_matches_oracle_live():
+    """AuroraWave through `rollout` (hook applied once to the initial state, NaN fields fed back as density
+    channels, LoRA from the second step) against the CPU oracle on the same inputs."""
+    import aurora_b200 as ab
+    from oracle import aurora_oracle as O
+
+    cfg, model = _build("tiny_wave", "AuroraWave", 9)
+    sd = fx.make_state_dict(cfg, seed=9)
+    batch = fx.make_wave_batch(cfg, 33, 64, seed=9, rollout_step=0, with_dwi=True)
+    with torch.inference_mode():
+        refs = list(O.rollout(cfg, sd, batch, steps=2, dtype=torch.float32, variant="wave", variant_args=fx.WAVE_ARGS))
+    for i, pred in enumerate(ab.rollout(model, batch, steps=2)):
+        assert pred.metadata.rollout_step == i + 1
+        assert list(pred.surf_vars) == list(refs[i].surf_vars)
+        for grp, d, r in (("surf", pred.surf_vars, refs[i].surf_vars), ("atmos", pred.atmos_vars, refs[i].atmos_vars)):
+            for k in d:
+                err, nan_mismatch = fx.field_error(d[k].cpu(), r[k], angle=k in fx.WAVE_ANGLES)
+                assert err < TOL * (i + 1) and nan_mismatch < NAN_TOL * (i + 1), (i, grp, k, err, nan_mismatch)
 
 
 def test_no_cpu_path():

@@ -18,15 +18,10 @@ GOLD = Path(__file__).parent / "golden"
 
 
 def _run(name, dtype):
-    cfg_name, cls_name, h, w, levels, bsz, step, seed = MODEL_CASES[name]
-    cfg = fx.CONFIGS[cfg_name]
-    extra = fx.air_extra_specs(cfg) if cls_name == "AuroraAirPollution" else ()
-    sd = fx.make_state_dict(cfg, seed=seed, extra=extra)
-    batch = fx.make_batch(cfg, h, w, levels=levels, b=bsz, seed=seed, rollout_step=step)
+    cfg, sd, batch, variant, vargs, _ = fx.case_inputs(MODEL_CASES[name])
     taps = {}
-    variant = "air_pollution" if cls_name == "AuroraAirPollution" else "base"
     with torch.inference_mode():
-        pred = O.forward(cfg, sd, batch, dtype=dtype, taps=taps, variant=variant)
+        pred = O.forward(cfg, sd, batch, dtype=dtype, taps=taps, variant=variant, variant_args=vargs)
     return pred, taps
 
 
@@ -42,21 +37,25 @@ def test_oracle_fp64_matches_reference(name):
     for grp, d in (("surf", pred.surf_vars), ("atmos", pred.atmos_vars)):
         keys = [k[len(grp) + 1:] for k in gold.files if k.startswith(grp + ".")]
         assert sorted(keys) == sorted(d.keys())
+        if MODEL_CASES[name][1] == "AuroraWave":
+            assert list(d.keys()) == keys  # the hooks' dict order (angles re-appended last) is part of the contract
         for k in keys:
             ref = torch.from_numpy(gold[f"{grp}.{k}"])
             assert d[k].shape == ref.shape
-            err = fx.rel_mean_abs(d[k], ref)
-            assert err < 2e-7, (grp, k, err)
+            err, nan_mismatch = fx.field_error(d[k], ref, angle=k in fx.WAVE_ANGLES)
+            assert err < 2e-7 and nan_mismatch == 0.0, (grp, k, err, nan_mismatch)
+            if MODEL_CASES[name][1] == "AuroraWave" and k in fx.WAVE_VARS:
+                assert torch.isnan(ref).any() and not torch.isnan(ref).all(), k  # the fixture exercises both sides
 
 
-@pytest.mark.parametrize("name", ["tiny_33x64", "small_17x32", "tiny_air_46x90"])
+@pytest.mark.parametrize("name", ["tiny_33x64", "small_17x32", "tiny_air_46x90", "tiny_wave_33x64"])
 def test_oracle_fp32_within_reference_spread(name):
     gold = np.load(GOLD / f"model_{name}.npz")
     pred, _ = _run(name, torch.float32)
     for grp, d in (("surf", pred.surf_vars), ("atmos", pred.atmos_vars)):
         for k, v in d.items():
-            err = fx.rel_mean_abs(v, torch.from_numpy(gold[f"{grp}.{k}"]))
-            assert err < 1e-5, (grp, k, err)
+            err, nan_mismatch = fx.field_error(v, torch.from_numpy(gold[f"{grp}.{k}"]), angle=k in fx.WAVE_ANGLES)
+            assert err < 1e-5 and nan_mismatch < 1e-3, (grp, k, err, nan_mismatch)
 
 
 def test_oracle_rollout_matches_reference():
