@@ -194,7 +194,10 @@ def gemm(
         g.ld_bf16 = _ld(out_bf16)
         g.out_dtype = _dt(out_bf16)
     g.act = act
-    with _Timed("gemm", work=2.0 * m * n * k):
+    # compulsory HBM bytes: A and W once, every output once, the residual once
+    nb = 2.0 * m * k + 2.0 * n * k + m * n * ((4.0 if out_f32 is not None else 0.0) + (2.0 if out_bf16 is not None else 0.0)
+                                              + (4.0 if residual is not None else 0.0))
+    with _Timed("gemm", work=2.0 * m * n * k, nbytes=nb):
         check(lib().ab_gemm_bf16(C.byref(g), C.c_void_p(stream_ptr())), "ab_gemm_bf16")
 
 

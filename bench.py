@@ -14,9 +14,9 @@
 * `--impl reference`: the reference algorithm's CPU implementation (oracle port; the Python reference
   itself cannot travel to the GPU box) on the host cores, each step a bounded sample extrapolated by
   algorithmic FLOPs.
-* N > 1: the forward pass does not need a collective for independent forecasts, so each rank runs its own
-  replica of the workload ("weak" scaling; latitude sharding of ONE forecast is designed in DESIGN.md but
-  not implemented yet).
+* N > 1: the forward pass does not need a collective for independent forecasts, so by default each rank runs
+  its own replica of the workload ("weak" scaling, no data-path collective).  `--parallelism latshard` instead
+  shards ONE forecast over the N GPUs by latitude band with an NCCL halo exchange per Swin block ("strong").
 
 Synthetic data (ERA5-shaped, `loc + scale * N(0,1)` per variable / level) and random weights with the
 reference's zero-initialised tensors re-drawn (otherwise every Swin block is an identity).
@@ -172,18 +172,37 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU baseline (oracle port) — bounded sample
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline_sample(workload: str, cores: int) -> dict:
+_THREADS: dict = {}
+
+
+def pick_threads(workload: str, cores: int) -> int:
+    """Host threads for the CPU legs: the fastest of {cores, cores/2, cores/4} on a small slice of the sample
+    (PyTorch's CPU kernels do not always scale to every hardware thread of a large box)."""
+    if workload not in _THREADS:
+        best = None
+        for n in sorted({max(1, cores), max(1, cores // 2), max(1, cores // 4)}, reverse=True):
+            t = cpu_baseline_sample(workload, n, lat_fraction=6, calibrate=True)["sample_seconds"]
+            if best is None or t < best[0]:
+                best = (t, n)
+        _THREADS[workload] = best[1]
+    return _THREADS[workload]
+
+
+def cpu_baseline_sample(workload: str, cores: int, lat_fraction: int = 1, calibrate: bool = False) -> dict:
     """Time the CPU oracle on a bounded sample of the workload and extrapolate by algorithmic FLOPs.
 
     Sample: one Swin3D block of every U-Net stage (unshifted for stage 1, shifted for stages 2-3) at the
-    workload's real token grid and widths, fp32, `cores` host threads.  Blocks are ~84 % of the step's FLOPs
-    and cost the same ~1.7 TFLOP at every stage; the step time is the sample time scaled by
-    (total step FLOPs / sample FLOPs)."""
+    workload's real widths and token grid, fp32, `cores` host threads; `lat_fraction` > 1 keeps only the first
+    1 / lat_fraction of the latitude rows of every stage (whole window rows) to bound the sample further.
+    Blocks are ~84 % of the step's FLOPs and cost the same ~1.7 TFLOP at every stage; the step time is the
+    sample time scaled by (total step FLOPs / sample FLOPs)."""
     from oracle import aurora_oracle as O
     import aurora_b200 as ab
 
     cls, h, w, levels = WORKLOADS[workload]
     model_cfg = getattr(ab, cls)(_init="empty").config
+    if not calibrate:
+        cores = pick_threads(workload, cores)
     torch.set_num_threads(cores)
     p = model_cfg.patch_size
     res0 = (model_cfg.latent_levels, (h - h % p) // p, w // p)
@@ -192,6 +211,9 @@ def cpu_baseline_sample(workload: str, cores: int) -> dict:
     sample_flops, t_total, parts = 0.0, 0.0, []
     c = torch.randn(1, model_cfg.embed_dim, generator=g)
     for i, res in enumerate(all_res):
+        if lat_fraction > 1:
+            wh = model_cfg.window_size[1]
+            res = (res[0], max(wh, (res[1] // lat_fraction) // wh * wh), res[2])
         d = model_cfg.embed_dim * 2**i
         heads = model_cfg.encoder_num_heads[i]
         l = res[0] * res[1] * res[2]
@@ -202,14 +224,16 @@ def cpu_baseline_sample(workload: str, cores: int) -> dict:
             f"{pre}.norm2.ln_modulation.1.weight": torch.randn(2 * d, model_cfg.embed_dim, generator=g) * 0.02,
             f"{pre}.norm2.ln_modulation.1.bias": torch.randn(2 * d, generator=g) * 0.1,
             f"{pre}.attn.qkv.weight": torch.randn(3 * d, d, generator=g) * 0.02,
-            f"{pre}.attn.qkv.bias": torch.zeros(3 * d),
+            f"{pre}.attn.qkv.bias": torch.randn(3 * d, generator=g) * 0.02,
             f"{pre}.attn.proj.weight": torch.randn(d, d, generator=g) * 0.02,
-            f"{pre}.attn.proj.bias": torch.zeros(d),
+            f"{pre}.attn.proj.bias": torch.randn(d, generator=g) * 0.02,
             f"{pre}.mlp.fc1.weight": torch.randn(4 * d, d, generator=g) * 0.02,
-            f"{pre}.mlp.fc1.bias": torch.zeros(4 * d),
+            f"{pre}.mlp.fc1.bias": torch.randn(4 * d, generator=g) * 0.02,
             f"{pre}.mlp.fc2.weight": torch.randn(d, 4 * d, generator=g) * 0.02,
-            f"{pre}.mlp.fc2.bias": torch.zeros(d),
+            f"{pre}.mlp.fc2.bias": torch.randn(d, generator=g) * 0.02,
         }
+        # (non-zero biases like any trained checkpoint: with zero biases the zero-padded tokens of shifted windows
+        # produce denormal attention outputs, which slow the CPU GEMMs down several-fold)
         x = torch.randn(1, l, d, generator=g)
         cfg_nolora = type(model_cfg)(**{**model_cfg.__dict__, "use_lora": False})
         with torch.inference_mode():
@@ -231,10 +255,26 @@ def cpu_baseline_sample(workload: str, cores: int) -> dict:
     step_flops = ALGO_TFLOP[workload] * 1e12
     est_step_s = t_total * step_flops / sample_flops
     return {"value": 1.0 / est_step_s, "unit": "forecast-steps/s", "cores": cores, "kind": "port",
-            "sample": f"one Swin3D block per U-Net stage at full size ({'; '.join(parts)}), fp32, "
+            "sample": f"one Swin3D block per U-Net stage at full width"
+                      f"{'' if lat_fraction == 1 else f', first 1/{lat_fraction} of the latitude rows'} "
+                      f"({'; '.join(parts)}), fp32, "
                       f"{sample_flops / 1e12:.2f} of {step_flops / 1e12:.1f} TFLOP; step time extrapolated by FLOPs "
                       f"= {est_step_s:.1f} s",
             "sample_seconds": t_total}
+
+
+def gemm_traffic(workload: str, launches: int, algo_bytes: float) -> dict:
+    """`traffic` of the roofline object: DRAM bytes (read + write) per GEMM launch from the committed ncu pass
+    over one step of this workload (profiles/gemm_traffic.json, written by tools/ncu_traffic.py from the ncu CSV;
+    bench.py cannot run ncu itself), next to the compulsory bytes per launch counted from the launch arguments."""
+    out = {"traffic": None, "algorithmic_bytes": algo_bytes / launches if launches else None}
+    f = ROOT / "profiles" / "gemm_traffic.json"
+    if f.exists():
+        rec = json.loads(f.read_text()).get(workload)
+        if rec:
+            out["traffic"] = rec["dram_bytes_per_launch"]
+            out["traffic_source"] = rec["source"]
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -245,8 +285,12 @@ def run_reference_arm(args) -> None:
     cores = os.cpu_count() or 1
     vals, ms = [], []
     base = None
-    for i in range(args.warmup + args.steps):
-        base = cpu_baseline_sample(args.workload, cores)
+    # one full-size sample costs ~25 s on 128 cores; keep the whole run within a few minutes by shrinking the
+    # latitude extent of the per-step sample when many steps are asked for
+    n_samples = args.warmup + args.steps
+    lat_fraction = 1 if n_samples <= 4 else 2 if n_samples <= 8 else 4
+    for i in range(n_samples):
+        base = cpu_baseline_sample(args.workload, cores, lat_fraction)
         if i >= args.warmup:
             vals.append(base["value"])
     v = statistics.mean(vals)
@@ -373,14 +417,15 @@ def main() -> None:
         t = sum(a.elapsed_time(b) for a, b, _, _ in rows) / 1e3
         return len(rows), t, sum(r[2] for r in rows), sum(r[3] for r in rows)
 
-    n_g, t_g, f_g, _ = agg("gemm")
+    n_g, t_g, f_g, b_g = agg("gemm")
     n_a, t_a, f_a, b_a = agg("window_attention")
     n_l, t_l, _, b_l = agg("ln_mod_residual")
     peak_tf = pk["bf16_tflops_sustained"] or pk["bf16_tflops"]
     roofline = {
         "kernel": "gemm_bf16_tn_kernel (tcgen05)", "bound": "tensor",
         "achieved": f_g / t_g / 1e12 if t_g else None, "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": (f_g / t_g / 1e12) / peak_tf if t_g else None, "traffic": None,
+        "frac": (f_g / t_g / 1e12) / peak_tf if t_g else None,
+        **gemm_traffic(args.workload, n_g, b_g),
         "peak_source": pk["source"] + " (sustained figure: kernel timed inside a long step)",
         "launches_per_step": n_g, "seconds_per_step": t_g, "share_of_step": t_g / (ms / 1e3),
         "others": {
@@ -390,6 +435,10 @@ def main() -> None:
                 "frac_hbm": (b_a / t_a / 1e9) / pk["hbm_gbs"] if t_a else None,
                 "achieved_tflops": f_a / t_a / 1e12 if t_a else None,
                 "frac_tensor": (f_a / t_a / 1e12) / pk["bf16_tflops"] if t_a else None,
+                # stand-alone roofline of this kernel: min(tensor peak, HBM peak x 72 FLOP/B)
+                "standalone_roofline_tflops": min(pk["bf16_tflops"], pk["hbm_gbs"] * (f_a / b_a) / 1e3) if b_a else None,
+                "frac_standalone_roofline": ((f_a / t_a / 1e12) / min(pk["bf16_tflops"], pk["hbm_gbs"] * (f_a / b_a) / 1e3)
+                                             if t_a and b_a else None),
             },
             "ln_mod_residual": {
                 "bound": "hbm", "launches_per_step": n_l, "seconds_per_step": t_l, "share_of_step": t_l / (ms / 1e3),

@@ -28,6 +28,7 @@ inputs) by tests/golden/make_golden.py, whose stored outputs tests/test_oracle_g
 from __future__ import annotations
 
 import dataclasses
+import functools
 import math
 from datetime import timedelta
 from typing import Optional
@@ -198,6 +199,13 @@ def _ada_ln(sd, prefix, x, c):
     return _ln(x) * scale + shift
 
 
+@functools.lru_cache(maxsize=16)
+def _mask_tensor(res, ws0, ss0, dtype):
+    """Shifted-window mask as a tensor, memoised per geometry (the reference caches it too, swin3d.py:303)."""
+    m = W.shifted_window_mask(res, ws0, ss0, warped=True)
+    return None if m is None else torch.from_numpy(np.array(m)).to(dtype)
+
+
 def swin_block(sd, prefix, x, c, res, num_heads, shifted, cfg: ModelConfig, step: int, taps=None):
     """One Swin3D block (swin3d.py:440-509) via the closed-form gather map of oracle/windows.py."""
     b, l, d = x.shape
@@ -206,22 +214,30 @@ def swin_block(sd, prefix, x, c, res, num_heads, shifted, cfg: ModelConfig, step
     idx_np, ws, ss, _ = W.window_gather_map(res, ws0, ss0)
     idx = torch.from_numpy(idx_np)
     nw, n = idx.shape
-    valid = idx >= 0
-    xw = torch.zeros(b, nw, n, d, dtype=x.dtype)
-    xw[:, valid] = x[:, idx[valid]]  # zero rows where padded (they still get q = k = v = bias)
+    flat = idx.reshape(-1)
+    valid = flat >= 0
+    all_valid = bool(valid.all())
+    xw = x.index_select(1, flat.clamp_min(0))
+    if not all_valid:
+        xw = xw * valid[None, :, None].to(x.dtype)  # zero rows where padded (they still get q = k = v = bias)
+    xw = xw.reshape(b, nw, n, d)
     qkv = _lin(sd, f"{prefix}.attn.qkv", xw) + _lora_delta(sd, f"{prefix}.attn.lora_qkv", xw, cfg, step)
     hd = d // num_heads
     qkv = qkv.reshape(b, nw, n, 3, num_heads, hd).permute(3, 0, 1, 4, 2, 5)  # (3, B, nW, H, N, hd)
     q, k, v = qkv[0], qkv[1], qkv[2]
-    logits = q @ k.transpose(-1, -2) / math.sqrt(hd)
-    mask = W.shifted_window_mask(res, ws0, ss0, warped=True)
-    if mask is not None:
-        logits = logits + torch.from_numpy(mask).to(x.dtype)[None, :, None]
-    att = torch.softmax(logits, dim=-1) @ v
+    mask = _mask_tensor(tuple(res), ws0, ss0, x.dtype)
+    # softmax(q k^T / sqrt(hd) + mask) v, as the reference's F.scaled_dot_product_attention call (swin3d.py:159-166)
+    att = F.scaled_dot_product_attention(
+        q, k, v, attn_mask=None if mask is None else mask[None, :, None])
     att = att.permute(0, 1, 3, 2, 4).reshape(b, nw, n, d)
     out = _lin(sd, f"{prefix}.attn.proj", att) + _lora_delta(sd, f"{prefix}.attn.lora_proj", att, cfg, step)
-    y = torch.zeros_like(x)
-    y[:, idx[valid]] = out[:, valid]  # reverse partition + crop + un-roll == scatter through the same map
+    # reverse partition + crop + un-roll == scatter through the same map (every real token appears exactly once)
+    out = out.reshape(b, nw * n, d)
+    if all_valid:
+        y = torch.empty_like(x).index_copy_(1, flat, out)
+    else:
+        keep = valid.nonzero().squeeze(1)
+        y = torch.zeros_like(x).index_copy_(1, flat[keep], out.index_select(1, keep))
     if taps is not None:
         taps[f"{prefix}.attn_out"] = y
     x = x + _ada_ln(sd, f"{prefix}.norm1", y, c)

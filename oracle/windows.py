@@ -17,6 +17,8 @@ tests/golden/make_golden.py -> tests/golden/windows_*.npz; see tests/test_oracle
 
 from __future__ import annotations
 
+import functools
+
 import numpy as np
 
 PAD_GROUP = 27  # group id the reference assigns to zero-padded tokens (swin3d.py:348-352)
@@ -112,9 +114,18 @@ def window_group_ids(res, ws0, ss0, warped=True):
 
 
 def shifted_window_mask(res, ws0, ss0, warped=True, dtype=np.float32):
-    """(nW, N, N) additive mask: 0 inside a group, -100 across groups (swin3d.py:357-358)."""
+    """(nW, N, N) additive mask: 0 inside a group, -100 across groups (swin3d.py:357-358).  Memoised per
+    geometry like the reference's `lru_cache` on `compute_3d_shifted_window_mask` (swin3d.py:303); the
+    returned array is read-only."""
+    return _shifted_window_mask(tuple(res), tuple(ws0), tuple(ss0), bool(warped), np.dtype(dtype))
+
+
+@functools.lru_cache(maxsize=16)
+def _shifted_window_mask(res, ws0, ss0, warped, dtype):
     g = window_group_ids(res, ws0, ss0, warped)
     if g is None:
         return None
     same = g[:, :, None] == g[:, None, :]
-    return np.where(same, 0.0, -100.0).astype(dtype)
+    m = np.where(same, dtype.type(0.0), dtype.type(-100.0))
+    m.setflags(write=False)
+    return m
