@@ -49,12 +49,13 @@ WORKLOADS = {
     "aurora-small-17x32x4L": ("AuroraSmallPretrained", 17, 32, (100, 250, 500, 850)),
     "aurora-highres-0.1deg-1801x3600x13L": ("AuroraHighRes", 1801, 3600, LEVELS13),
     "aurora-airpollution-0.4deg-451x900x13L": ("AuroraAirPollution", 451, 900, LEVELS13),
+    "aurora-wave-0.25deg-721x1440x13L": ("AuroraWave", 721, 1440, LEVELS13),
 }
 DEFAULT_WORKLOAD = "aurora-0.25deg-721x1440x13L"
 
 # Algorithmic work of one forward step, 2 flops per MAC.
 ALGO_TFLOP = {"aurora-0.25deg-721x1440x13L": 96.8, "aurora-highres-0.1deg-1801x3600x13L": 91.7,
-              "aurora-airpollution-0.4deg-451x900x13L": 69.2,
+              "aurora-airpollution-0.4deg-451x900x13L": 69.2, "aurora-wave-0.25deg-721x1440x13L": 96.8,
               "aurora-small-0.25deg-721x1440x13L": 12.6, "aurora-small-17x32x4L": 0.004}
 
 
@@ -84,13 +85,23 @@ def make_host_batch(cfg, h, w, levels, pinned: bool, seed: int = 0):
         return t
 
     surf = {}
-    for k in cfg.surf_vars:
+    surf_names = cfg.surf_vars
+    wave = any(k.endswith("_density") for k in surf_names)
+    if wave:  # AuroraWave takes the raw HRES-WAM names; absent wave components are NaN (here: a band of "land")
+        surf_names = tuple(dict.fromkeys(k.removesuffix("_density").removesuffix("_sin").removesuffix("_cos")
+                                         for k in surf_names))
+    for k in surf_names:
         loc, sc = surf_stats_of(k)
         surf[k] = alloc((1, 2, h, w)).mul_(sc).add_(loc)
+        if wave and k not in ("2t", "10u", "10v", "msl", "wind"):
+            surf[k].abs_().clamp_(min=0.05)
+            surf[k][..., :, : w // 4] = float("nan")
     static = {}
     for k in cfg.static_vars:
         loc, sc = surf_stats_of(k)
         static[k] = alloc((h, w)).mul_(sc).add_(loc)
+        if k in ("wmb", "lat_mask"):
+            static[k].copy_((static[k] > -1.0).float())
     atmos = {}
     for k in cfg.atmos_vars:
         locs, scs = atmos_stats_of(k, levels)
@@ -319,6 +330,8 @@ def main() -> None:
     ap.add_argument("--parallelism", default="replicas", choices=["replicas", "latshard"],
                     help="N > 1: independent forecasts per GPU (default) or ONE forecast sharded by latitude")
     ap.add_argument("--cuda-graph", action="store_true", help="model.use_cuda_graph = True (step replayed from a graph)")
+    ap.add_argument("--rollout", type=int, default=0, metavar="N",
+                    help="also time one N-step autoregressive rollout (BASELINE configs[2]: 40) and add a `rollout` object")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -374,15 +387,15 @@ def main() -> None:
     barrier()
     launches0 = cabi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
-        e0.record()
-        for _ in range(args.steps):
-            pred = model.forward(dev_batch)
-        e1.record()
-        barrier()
+    clk = ClockSampler(local_rank)   # samples through BOTH timed regions (device-resident and end-to-end)
+    clk.__enter__()
+    e0.record()
+    for _ in range(args.steps):
+        pred = model.forward(dev_batch)
+    e1.record()
+    barrier()
     launches = cabi.launch_count() - launches0
     ms = e0.elapsed_time(e1) / args.steps
-    clocks = clk.summary()
 
     # ---- end to end through the public API from pinned host memory ----
     e2e_ms = None
@@ -402,6 +415,27 @@ def main() -> None:
         e1.record()
         barrier()
         e2e_ms = e0.elapsed_time(e1) / args.steps
+    clk.__exit__()
+    clocks = clk.summary()
+
+    # ---- autoregressive rollout (rollout.py:14-49): state stays on the device, every prediction is yielded ----
+    rollout_info = None
+    if args.rollout > 0 and not latshard:
+        def run_rollout(n):
+            last = None
+            for p in ab.rollout(model, host_batch, steps=n):   # initial H2D inside; the caller keeps only the last step
+                last = p
+            return last
+        run_rollout(2)
+        barrier()
+        e0.record()
+        run_rollout(args.rollout)
+        e1.record()
+        barrier()
+        r_ms = e0.elapsed_time(e1)
+        rollout_info = {"steps": args.rollout, "ms_total": r_ms, "ms_per_step": r_ms / args.rollout,
+                        "value": world * 1000.0 * args.rollout / r_ms, "unit": "forecast-steps/s",
+                        "note": "aurora_b200.rollout from a pinned host batch; history slide and predictions on the device"}
 
     # ---- per-kernel timing for the roofline (one instrumented step; CUDA events around each launch) ----
     cabi.PROFILE = {}
@@ -484,6 +518,10 @@ def main() -> None:
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
+        if rollout_info is not None:
+            if distributed:
+                rollout_info["note"] += " (rank 0's time)"
+            line["rollout"] = rollout_info
         print(json.dumps(line), flush=True)
     if distributed:
         dist.destroy_process_group()

@@ -46,13 +46,16 @@ def main() -> None:
         per_launch[int(r["ID"])]["name"] = r["Kernel Name"]
         per_launch[int(r["ID"])][r["Metric Name"]] = val * scale
     agg: dict = defaultdict(lambda: [0, 0.0, 0.0, 0.0])
+    mine = set()
     for rec in per_launch.values():
+        if "ab::" in rec["name"]:  # also kernels of nested namespaces whose printed name drops the `ab::` prefix
+            mine.add(short(rec["name"]))
         a = agg[short(rec["name"])]
         a[0] += 1
         a[1] += rec.get("gpu__time_duration.sum", 0.0)
         a[2] += rec.get("dram__bytes_read.sum", 0.0)
         a[3] += rec.get("dram__bytes_write.sum", 0.0)
-    ours = {k: v for k, v in agg.items() if "ab::" in k}
+    ours = {k: v for k, v in agg.items() if k in mine}
     total_ns = sum(v[1] for v in ours.values())
     out = [f"# {args.tag} — ncu launch list of `bench.py --steps 1 --warmup 1` ({args.workload})",
            f"kernels of libaurora_b200.so only; {sum(v[0] for v in ours.values())} launches over the captured steps "
@@ -63,7 +66,7 @@ def main() -> None:
     for k, v in sorted(ours.items(), key=lambda kv: -kv[1][1]):
         out.append(f"| `{k}` | {v[0]} | {v[1] / 1e6:.3f} | {100 * v[1] / total_ns:.1f}% | {v[2] / 1e9:.2f} | "
                    f"{v[3] / 1e9:.2f} | {(v[2] + v[3]) / v[0] / 1e6:.1f} |")
-    other = {k: v for k, v in agg.items() if "ab::" not in k}
+    other = {k: v for k, v in agg.items() if k not in mine}
     out += ["", f"other kernels (PyTorch fills / copies): {sum(v[0] for v in other.values())} launches, "
                 f"{sum(v[1] for v in other.values()) / 1e6:.2f} ms"]
     (ROOT / "profiles" / f"{args.tag}_launch_list.md").write_text("\n".join(out) + "\n")
