@@ -21,7 +21,6 @@ There is NO CPU path: tensors that are not on a CUDA device raise.
 from __future__ import annotations
 
 import dataclasses
-import math
 from datetime import timedelta
 from typing import Optional
 

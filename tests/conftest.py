@@ -1,6 +1,5 @@
 """pytest configuration: the ``gpu`` marker and a few shared helpers."""
 
-import os
 import sys
 from pathlib import Path
 

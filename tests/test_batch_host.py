@@ -9,7 +9,7 @@ from pathlib import Path
 import pytest
 import torch
 
-from aurora_b200 import Batch, Metadata
+from aurora_b200 import Metadata
 from aurora_b200 import stats
 from tests import fixtures as fx
 

@@ -13,7 +13,6 @@ import numpy as np
 import pytest
 
 from aurora_b200 import cabi
-from oracle import windows as W
 
 ROOT = Path(__file__).resolve().parent.parent
 GOLD = Path(__file__).parent / "golden"
