@@ -100,6 +100,7 @@ class AuroraEngine:
         self.shard_group = None  # torch.distributed group used by forward(..., sharded=True)
         self.use_cuda_graph = False  # replay the step from a captured CUDA graph (outputs become static buffers)
         self._graphs: dict = {}
+        self._capture: Optional[dict] = None  # state of a running segmented graph capture (see _exchange)
         self.variant = variant
         some = next(iter(params.values()))
         if not some.is_cuda:
@@ -509,7 +510,7 @@ class AuroraEngine:
             h_begin, h_global = slab
             c_, rows_, w_ = res
             halo = self._buffer("bb.halo", (2, c_, sharding.HALO, w_ * 3 * d), torch.bfloat16)
-            sharding.exchange_halo(qkv.view(c_, rows_, w_ * 3 * d), sharding.HALO, out=halo, group=self.shard_group)
+            self._exchange(qkv.view(c_, rows_, w_ * 3 * d), halo)
             cabi.window_attention(qkv, att, batch=1, res=(c_, h_global, w_), window=ws, shift=ss, num_heads=heads,
                                   pad_qkv=pad, slab=(h_begin, rows_),
                                   halo_qkv=halo.view(2, c_, sharding.HALO, w_, 3 * d))
@@ -522,6 +523,25 @@ class AuroraEngine:
         sc2, sh2 = self._modulation(f"{prefix}.norm2", d)
         cabi.ln_mod_residual(y, scale=sc2, shift=sh2, residual=x_f32, out_f32=x_f32,
                              out_bf16=x_b16 if out_b16 is None else out_b16)
+
+    def _exchange(self, local: torch.Tensor, halo: torch.Tensor) -> None:
+        """The one exchange step of a sharded forecast (sharding.exchange_halo).  While a step is being captured
+        for graph replay the NCCL point-to-point calls stay OUTSIDE the graphs: the running graph segment is
+        closed, the exchange runs eagerly and is remembered as a host callable, and a new segment is opened, so a
+        replayed step is `graph, exchange, graph, exchange, ..., graph` (49 graph launches + 48 exchanges instead
+        of ~530 host-side launches)."""
+        def run():
+            sharding.exchange_halo(local, sharding.HALO, out=halo, group=self.shard_group)
+
+        cap = self._capture
+        if cap is None:
+            run()
+            return
+        cap["graph"].capture_end()
+        run()
+        cap["items"] += [cap["graph"], run]
+        cap["graph"] = torch.cuda.CUDAGraph()
+        cap["graph"].capture_begin(pool=cap["pool"], capture_error_mode="thread_local")
 
     def _backbone(self, x_f32: torch.Tensor, x_b16: torch.Tensor, patch_res, rollout_step: int,
                   plan: Optional["sharding.SlabPlan"] = None) -> torch.Tensor:
@@ -755,13 +775,13 @@ class AuroraEngine:
         computes only its latitude band of the forecast (`sharding.plan_slabs`) and returns that band; the
         result carries `.slab_plans` for `sharding.gather_bands`.
 
-        With `self.use_cuda_graph` the device work of the step (about 480 kernel launches and, when sharded, 48
-        NCCL halo exchanges) is captured once per input signature and replayed; outputs then live in static
-        buffers that the next call overwrites."""
+        With `self.use_cuda_graph` the device work of the step (about 480 kernel launches) is captured once per
+        input signature and replayed; outputs then live in static buffers that the next call overwrites.  A
+        sharded step is captured as 49 graph segments with the 48 NCCL halo exchanges issued eagerly between
+        them (capturing NCCL point-to-point calls inside a graph deadlocked on the test pod, torch 2.11 /
+        NCCL 2.28)."""
         prep = self._prepare(batch, sharded)
-        # Graph replay is single-GPU only: capturing the NCCL point-to-point halo exchange deadlocked on the
-        # test pod (torch 2.11 / NCCL 2.28), so sharded steps always launch eagerly.
-        if self.use_cuda_graph and not self.cfg.dynamic_vars and not sharded:
+        if self.use_cuda_graph and not self.cfg.dynamic_vars:
             return self._run_graph(prep)
         return self._finish(prep, *self._run(prep))
 
@@ -885,10 +905,22 @@ class AuroraEngine:
             sprep = dict(prep, batch=static, abs_emb=prep["abs_emb"].clone())
             self._run(sprep)
             torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                outs = self._run(sprep)
-            entry = {"graph": graph, "prep": sprep, "outs": outs}
+            # Segmented capture on a side stream: `_exchange` splits the step at every halo exchange.  All
+            # segments share one memory pool; an unsharded step is a single segment.
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                cap = {"pool": torch.cuda.graph_pool_handle(), "items": [], "graph": torch.cuda.CUDAGraph()}
+                cap["graph"].capture_begin(pool=cap["pool"], capture_error_mode="thread_local")
+                self._capture = cap
+                try:
+                    outs = self._run(sprep)
+                    cap["graph"].capture_end()
+                finally:
+                    self._capture = None
+                items = cap["items"] + [cap["graph"]]
+            torch.cuda.current_stream().wait_stream(side)
+            entry = {"items": items, "prep": sprep, "outs": outs}
             self._graphs[sig] = entry
         sprep = entry["prep"]
         sb = sprep["batch"]
@@ -898,5 +930,9 @@ class AuroraEngine:
                 if dst[k].data_ptr() != v.data_ptr():
                     dst[k].copy_(v)
         sprep["abs_emb"].copy_(prep["abs_emb"])
-        entry["graph"].replay()
+        for item in entry["items"]:
+            if isinstance(item, torch.cuda.CUDAGraph):
+                item.replay()
+            else:
+                item()  # halo exchange between two graph segments
         return self._finish(prep, *entry["outs"])

@@ -139,3 +139,26 @@ def test_cuda_graph_replay_is_bit_identical_to_eager():
     g1b = {k: v.clone() for k, v in model.forward(b1).atmos_vars.items()}  # replay again
     for k in e1:
         assert torch.equal(e1[k], g1[k]) and torch.equal(e2[k], g2[k]) and torch.equal(e1[k], g1b[k]), k
+
+
+def test_sharded_step_replays_from_graph_segments():
+    """A latitude-sharded step under `use_cuda_graph` is captured as graph segments with the halo exchanges issued
+    eagerly between them.  On one GPU (world size 1) the band is the whole grid and the halo wraps onto itself, so
+    the segmented replay must reproduce the eager sharded step and the plain forward bit for bit."""
+    cfg, model = _build("tiny_lora", "Aurora", 17)
+    # patch_res (4, 48, 64): full 144-token windows at all three stages (the tcgen05 slab kernel)
+    b1 = fx.make_batch(cfg, 192, 256, levels=fx.LEVELS4, b=1, seed=17, rollout_step=1)
+    b2 = fx.make_batch(cfg, 192, 256, levels=fx.LEVELS4, b=1, seed=18, rollout_step=1)
+    plain = {k: v.clone() for k, v in model.forward(b1).atmos_vars.items()}
+    eager1 = {k: v.clone() for k, v in model.forward(b1, sharded=True).atmos_vars.items()}
+    eager2 = {k: v.clone() for k, v in model.forward(b2, sharded=True).atmos_vars.items()}
+    model.use_cuda_graph = True
+    g1 = {k: v.clone() for k, v in model.forward(b1, sharded=True).atmos_vars.items()}   # capture + first replay
+    g2 = {k: v.clone() for k, v in model.forward(b2, sharded=True).atmos_vars.items()}   # replay, other inputs
+    g1b = {k: v.clone() for k, v in model.forward(b1, sharded=True).atmos_vars.items()}
+    entry = next(e for sig, e in model._engine._graphs.items() if sig[-2])  # the sharded signature
+    n_graphs = sum(isinstance(i, torch.cuda.CUDAGraph) for i in entry["items"])
+    assert n_graphs == 12 + 1 and len(entry["items"]) == 2 * 12 + 1  # 12 Swin blocks -> 12 exchanges, 13 segments
+    for k in plain:
+        assert torch.equal(plain[k], eager1[k]), k
+        assert torch.equal(eager1[k], g1[k]) and torch.equal(eager2[k], g2[k]) and torch.equal(eager1[k], g1b[k]), k

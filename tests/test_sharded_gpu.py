@@ -40,6 +40,14 @@ def _worker(rank, world, port, q):
     full_atmos = {k: sharding.gather_bands(v, plans, cfg.patch_size) for k, v in local.atmos_vars.items()}
     torch.cuda.synchronize()
     ok, worst = True, 0.0
+    # the same sharded step replayed from graph segments (NCCL exchanges eager between them): identical bits
+    keep = {k: v.clone() for k, v in local.atmos_vars.items()}
+    model.use_cuda_graph = True
+    for _ in range(2):  # capture + replay, then replay only
+        again = model.forward(batch, sharded=True)
+        torch.cuda.synchronize()
+        ok = ok and all(torch.equal(again.atmos_vars[k], keep[k]) for k in keep)
+    model.use_cuda_graph = False
     if rank == 0:
         ref = model.forward(batch)
         for grp, got in ((ref.surf_vars, full_surf), (ref.atmos_vars, full_atmos)):
