@@ -57,6 +57,16 @@ class Metadata:
         else:
             raise ValueError("The latitudes and longitudes must either both be vectors or both be matrices.")
 
+    @classmethod
+    def derived(cls, lat: torch.Tensor, lon: torch.Tensor, time, atmos_levels, rollout_step: int = 0) -> "Metadata":
+        """Metadata whose coordinates come from an already validated instance through a value-preserving step
+        (dtype cast, device move, dropping the last latitude row, a latitude band, the next time step): the checks
+        of `__post_init__` are not repeated.  On CUDA tensors each of them is a device synchronisation, which
+        would stall the launch queue once per forward step."""
+        m = object.__new__(cls)
+        m.lat, m.lon, m.time, m.atmos_levels, m.rollout_step = lat, lon, time, atmos_levels, rollout_step
+        return m
+
 
 def _affine(x: torch.Tensor, loc, scale, inverse: bool) -> torch.Tensor:
     return x * scale + loc if inverse else (x - loc) / scale
@@ -130,7 +140,7 @@ class Batch:
         if h % patch_size == 1:
             cut = lambda _k, v: v[..., :-1, :]  # noqa: E731
             out = self._map_vars(cut, cut, cut)
-            out.metadata = Metadata(
+            out.metadata = Metadata.derived(
                 lat=self.metadata.lat[:-1],
                 lon=self.metadata.lon,
                 atmos_levels=self.metadata.atmos_levels,
@@ -147,7 +157,7 @@ class Batch:
             surf_vars={k: f(v) for k, v in self.surf_vars.items()},
             static_vars={k: f(v) for k, v in self.static_vars.items()},
             atmos_vars={k: f(v) for k, v in self.atmos_vars.items()},
-            metadata=Metadata(
+            metadata=Metadata.derived(
                 lat=f(self.metadata.lat),
                 lon=f(self.metadata.lon),
                 atmos_levels=self.metadata.atmos_levels,

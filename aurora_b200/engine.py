@@ -127,6 +127,8 @@ class AuroraEngine:
         self._lora: dict = {}   # lora index -> merged qkv/proj weights
         self._grid_cache: Optional[tuple] = None
         self._level_cache: dict = {}
+        self._abs_cache: dict = {}   # times -> absolute-time embedding (B, D)
+        self._h2d: Optional[dict] = None  # double-buffered device copies of pinned host batches (see _upload_pinned)
         self._prepare_static()
 
     # ------------------------------------------------------------------------------------------
@@ -253,21 +255,29 @@ class AuroraEngine:
     # ------------------------------------------------------------------------------------------
     # cached location-independent encodings
     # ------------------------------------------------------------------------------------------
-    def _pos_scale_embed(self, lat: torch.Tensor, lon: torch.Tensor) -> torch.Tensor:
-        """pos_embed(pos_enc) + scale_embed(scale_enc), (L, D) f32 (encoder.py:334-346); cached per grid."""
+    def _pos_scale_embed(self, lat: torch.Tensor, lon: torch.Tensor, host=None) -> torch.Tensor:
+        """pos_embed(pos_enc) + scale_embed(scale_enc), (L, D) f32 (encoder.py:334-346); cached per grid.
+        `host` = (lat, lon) copies on the CPU when the caller has them (batches that arrived in host memory): the
+        cache lookup then compares on the host instead of synchronising the device."""
         c = self._grid_cache
         if c is not None and c[0].shape == lat.shape and c[1].shape == lon.shape:
             if c[0] is lat and c[1] is lon:
                 return c[2]
-            if torch.equal(c[0], lat) and torch.equal(c[1], lon):  # same grid, new tensor objects
-                self._grid_cache = (lat, lon, c[2])
+            if host is not None:
+                same = torch.equal(c[3], host[0].float()) and torch.equal(c[4], host[1].float())
+            else:
+                same = torch.equal(c[0], lat) and torch.equal(c[1], lon)  # same grid, new tensor objects
+            if same:
+                self._grid_cache = (lat, lon, c[2], c[3], c[4])
                 return c[2]
         d0 = self.cfg.embed_dim
-        pos, scale = E.pos_scale_encodings(d0, lat.detach().float().cpu(), lon.detach().float().cpu(), self.cfg.patch_size)
+        lat_h = (host[0] if host is not None else lat).detach().float().cpu()
+        lon_h = (host[1] if host is not None else lon).detach().float().cpu()
+        pos, scale = E.pos_scale_encodings(d0, lat_h, lon_h, self.cfg.patch_size)
         pos, scale = pos.to(self.device), scale.to(self.device)
         emb = cabi.linear_small(pos, self._f32("encoder.pos_embed.weight"), self._f32("encoder.pos_embed.bias"))
         emb = emb + cabi.linear_small(scale, self._f32("encoder.scale_embed.weight"), self._f32("encoder.scale_embed.bias"))
-        self._grid_cache = (lat, lon, emb.contiguous())
+        self._grid_cache = (lat, lon, emb.contiguous(), lat_h, lon_h)
         return self._grid_cache[2]
 
     def _level_embeds(self, levels: tuple) -> dict:
@@ -349,11 +359,21 @@ class AuroraEngine:
         """absolute_time_embed(absolute_time_expansion(t)) per batch element, (B, D) f32 (encoder.py:358-363).
         Host part (float64 Fourier expansion of `datetime.timestamp() / 3600`, like the reference) + a small
         fp32 linear on the device; kept outside the CUDA-graph-captured region."""
+        key = tuple(times)
+        hit = self._abs_cache.get(key)
+        if hit is not None:
+            return hit
         d0 = self.cfg.embed_dim
         abs_h = torch.tensor([tm.timestamp() / 3600 for tm in times], dtype=torch.float32)
-        abs_enc = E.fourier_expansion(abs_h, d0, E.ABS_TIME_RANGE, assert_range=False).to(self.device)
-        return cabi.linear_small(abs_enc, self._f32("encoder.absolute_time_embed.weight"),
-                                 self._f32("encoder.absolute_time_embed.bias"))
+        abs_enc = E.fourier_expansion(abs_h, d0, E.ABS_TIME_RANGE, assert_range=False)
+        # pinned staging + non-blocking copy: a pageable source would synchronise the stream once per step
+        abs_enc = abs_enc.pin_memory().to(self.device, non_blocking=True)
+        emb = cabi.linear_small(abs_enc, self._f32("encoder.absolute_time_embed.weight"),
+                                self._f32("encoder.absolute_time_embed.bias"))
+        if len(self._abs_cache) >= 64:
+            self._abs_cache.pop(next(iter(self._abs_cache)))
+        self._abs_cache[key] = emb
+        return emb
 
     def _encode(self, batch: Batch, b: int, x_f32: torch.Tensor, x_b16: torch.Tensor, abs_emb: torch.Tensor,
                 posscale: torch.Tensor) -> None:
@@ -782,12 +802,25 @@ class AuroraEngine:
         NCCL 2.28)."""
         prep = self._prepare(batch, sharded)
         if self.use_cuda_graph and not self.cfg.dynamic_vars:
-            return self._run_graph(prep)
-        return self._finish(prep, *self._run(prep))
+            pred = self._run_graph(prep)
+        else:
+            pred = self._finish(prep, *self._run(prep))
+        slot = prep["h2d_slot"]
+        if slot is not None:
+            # the prediction must not alias the upload buffers (they are overwritten two calls later) ...
+            pred.static_vars = {k: v.clone() for k, v in pred.static_vars.items()}
+            # ... and the set may be refilled only after every kernel of this step has read it
+            slot["busy"] = torch.cuda.Event()
+            slot["busy"].record(torch.cuda.current_stream())
+        return pred
 
     # -- eager part: dtype / crop / band slicing / H2D, everything that depends on host metadata ----------
     def _prepare(self, batch: Batch, sharded: bool) -> dict:
         cfg = self.cfg
+        slot = host_ll = None
+        if not sharded and self._is_pinned_host_batch(batch):
+            host_ll = (batch.metadata.lat, batch.metadata.lon)
+            batch, slot = self._upload_pinned(batch)  # full fields go up first (one DMA each); crop happens on the device
         batch = batch.type(torch.float32)
         batch = batch.crop(patch_size=cfg.patch_size)
         plans = plan = None
@@ -806,7 +839,7 @@ class AuroraEngine:
                 surf_vars={k: cut(v) for k, v in batch.surf_vars.items()},
                 static_vars={k: cut(v) for k, v in batch.static_vars.items()},
                 atmos_vars={k: cut(v) for k, v in batch.atmos_vars.items()},
-                metadata=Metadata(lat=lat[r0:r0 + nr] if lat.dim() == 1 else lat[r0:r0 + nr, :],
+                metadata=Metadata.derived(lat=lat[r0:r0 + nr] if lat.dim() == 1 else lat[r0:r0 + nr, :],
                                   lon=batch.metadata.lon, time=batch.metadata.time,
                                   atmos_levels=batch.metadata.atmos_levels, rollout_step=batch.metadata.rollout_step),
             )
@@ -827,9 +860,56 @@ class AuroraEngine:
             raise AssertionError(f"{t_hist} > {cfg.max_history_size}.")
         if sharded and bsz != 1:
             raise NotImplementedError("sharded forward supports batch size 1")
-        return {"batch": batch, "plan": plan, "plans": plans, "sharded": sharded,
+        return {"batch": batch, "plan": plan, "plans": plans, "sharded": sharded, "h2d_slot": slot,
                 "abs_emb": self._abs_time_embedding(batch.metadata.time),
-                "posscale": self._pos_scale_embed(batch.metadata.lat, batch.metadata.lon)}
+                "posscale": self._pos_scale_embed(
+                    batch.metadata.lat, batch.metadata.lon,
+                    host=None if host_ll is None else (host_ll[0][: batch.metadata.lat.shape[0]], host_ll[1]))}
+
+    # -- pinned host batches: uploads of step n+1 overlap the kernels of step n ---------------------------
+    @staticmethod
+    def _is_pinned_host_batch(batch: Batch) -> bool:
+        ts = [*batch.surf_vars.values(), *batch.static_vars.values(), *batch.atmos_vars.values()]
+        return bool(ts) and all((not t.is_cuda) and t.dtype == torch.float32 and t.is_contiguous() and t.is_pinned()
+                                for t in ts)
+
+    def _upload_pinned(self, batch: Batch):
+        """Host -> device copy of a batch held in PINNED host memory, on a dedicated copy stream into one of two
+        persistent device buffer sets.  The copies of this call do not queue behind the kernels of the previous
+        step (they only wait for the step that last read the same buffer set, two calls ago), so from the second
+        call on the upload runs under the previous step's compute.  The host waits for the copies before it
+        returns from here: when `forward` returns the caller may overwrite its host buffers, exactly as with the
+        reference's blocking `batch.to(device)` (aurora.py:281)."""
+        if self._h2d is None:
+            self._h2d = {"stream": torch.cuda.Stream(device=self.device), "turn": 0,
+                         "slots": [{"bufs": {}, "busy": None}, {"bufs": {}, "busy": None}]}
+        h = self._h2d
+        slot = h["slots"][h["turn"]]
+        h["turn"] ^= 1
+        cs = h["stream"]
+        if slot["busy"] is not None:
+            cs.wait_event(slot["busy"])  # kernels of the step that read this set have retired
+        out = {}
+        with torch.cuda.stream(cs):
+            for grp in ("surf_vars", "static_vars", "atmos_vars"):
+                out[grp] = {}
+                for k, v in getattr(batch, grp).items():
+                    key = (grp, k, tuple(v.shape))
+                    dst = slot["bufs"].get(key)
+                    if dst is None:
+                        dst = slot["bufs"][key] = torch.empty(v.shape, dtype=torch.float32, device=self.device)
+                    dst.copy_(v, non_blocking=True)
+                    out[grp][k] = dst
+            lat = batch.metadata.lat.to(self.device, non_blocking=True)
+            lon = batch.metadata.lon.to(self.device, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(cs)
+        done.synchronize()                               # host: the source buffers are free again
+        torch.cuda.current_stream().wait_event(done)     # device: compute starts after the upload
+        dev = Batch(out["surf_vars"], out["static_vars"], out["atmos_vars"],
+                    Metadata.derived(lat, lon, batch.metadata.time, batch.metadata.atmos_levels,
+                                     batch.metadata.rollout_step))
+        return dev, slot
 
     # -- device part: only kernel launches on the current stream (capturable) ----------------------------
     def _run(self, prep: dict):
@@ -870,7 +950,7 @@ class AuroraEngine:
             surf_vars=out_surf,
             static_vars=dict(batch.static_vars),
             atmos_vars=out_atmos,
-            metadata=Metadata(
+            metadata=Metadata.derived(
                 lat=batch.metadata.lat,
                 lon=batch.metadata.lon,
                 time=tuple(tm + self.cfg.timestep for tm in batch.metadata.time),

@@ -103,7 +103,16 @@ class Aurora(nn.Module):
     def _variant_args(self) -> dict:
         return {}
 
+    def _apply(self, fn, *a, **k):  # .to() / .cuda() / .float(): parameters may be re-created
+        self.__dict__.pop("_plist", None)
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self.__dict__.pop("_plist", None)
+        return super().load_state_dict(*a, **k)
+
     def _put(self, key: str, value: torch.Tensor) -> None:
+        self.__dict__.pop("_plist", None)
         path = key.split(".")
         if path[0] not in self._modules:
             self.add_module(path[0], _ParamNode())
@@ -113,9 +122,14 @@ class Aurora(nn.Module):
     def _get_engine(self):
         from aurora_b200.engine import AuroraEngine
 
-        params = dict(self.named_parameters())
-        sig = tuple((p.data_ptr(), p._version) for p in params.values())
+        # (address, version) of every parameter: a new engine is packed whenever a weight moved or was written to.
+        # The parameter list itself is cached (walking the module tree costs ~2 ms per forward on the 1.3 B model).
+        plist = self.__dict__.get("_plist")
+        if plist is None:
+            plist = self.__dict__["_plist"] = [p for _, p in self.named_parameters()]
+        sig = tuple((p.data_ptr(), p._version) for p in plist)
         if self._engine is None or sig != self._engine_sig:
+            params = dict(self.named_parameters())
             p0 = next(iter(params.values()))
             if p0.dtype != torch.float32:
                 raise NotImplementedError(

@@ -401,8 +401,8 @@ def main() -> None:
     e2e_ms = None
     if not args.no_e2e:
         def e2e_step():
-            b = host_batch.to(dev)            # H2D of every field (pinned source)
-            p = model.forward(b)
+            p = model.forward(host_batch)     # the public call on HOST tensors: H2D of every field happens inside
+                                              # (pinned source -> copy stream, overlaps the previous step's kernels)
             for grp in (p.surf_vars, p.atmos_vars):
                 for k, v in grp.items():
                     host_out[k].copy_(v, non_blocking=True)   # D2H of the whole prediction

@@ -162,3 +162,38 @@ def test_sharded_step_replays_from_graph_segments():
     for k in plain:
         assert torch.equal(plain[k], eager1[k]), k
         assert torch.equal(eager1[k], g1[k]) and torch.equal(eager2[k], g2[k]) and torch.equal(eager1[k], g1b[k]), k
+
+
+def _pin(batch):
+    from aurora_b200 import Batch
+
+    pin = lambda d: {k: v.contiguous().pin_memory() for k, v in d.items()}  # noqa: E731
+    return Batch(pin(batch.surf_vars), pin(batch.static_vars), pin(batch.atmos_vars), batch.metadata)
+
+
+@pytest.mark.parametrize("cfg_name,cls_name,h,w,levels", [("tiny_lora", "Aurora", 33, 64, fx.LEVELS4),
+                                                          ("tiny_air", "AuroraAirPollution", 45, 90, fx.LEVELS13)])
+def test_pinned_host_batches_take_the_overlapped_upload_and_give_the_same_bits(cfg_name, cls_name, h, w, levels):
+    """Batches in pinned host memory are uploaded on a copy stream into two alternating device buffer sets
+    (`AuroraEngine._upload_pinned`); five back-to-back steps on different inputs — no synchronisation in between, so
+    uploads overlap the previous step's kernels and both buffer sets are reused — must equal the pageable-memory
+    path bit for bit, and predictions must not alias the upload buffers."""
+    cfg, model = _build(cfg_name, cls_name, 23)
+    batches = [fx.make_batch(cfg, h, w, levels=levels, b=1, seed=40 + i, rollout_step=i % 2) for i in range(5)]
+    want = []
+    for b in batches:
+        p = model.forward(b)
+        want.append(({k: v.clone() for k, v in p.surf_vars.items()}, {k: v.clone() for k, v in p.atmos_vars.items()},
+                     {k: v.clone() for k, v in p.static_vars.items()}))
+    pinned = [_pin(b) for b in batches]
+    torch.cuda.synchronize()
+    preds = [model.forward(b) for b in pinned]          # no sync between the steps
+    torch.cuda.synchronize()
+    assert model._engine._h2d is not None and all(s["busy"] is not None for s in model._engine._h2d["slots"])
+    for p, (ws, wa, wst) in zip(preds, want):
+        for k in ws:
+            assert torch.equal(p.surf_vars[k], ws[k]), k
+        for k in wa:
+            assert torch.equal(p.atmos_vars[k], wa[k]), k
+        for k in wst:
+            assert torch.equal(p.static_vars[k], wst[k]), k
