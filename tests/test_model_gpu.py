@@ -171,8 +171,11 @@ def _pin(batch):
     return Batch(pin(batch.surf_vars), pin(batch.static_vars), pin(batch.atmos_vars), batch.metadata)
 
 
-@pytest.mark.parametrize("cfg_name,cls_name,h,w,levels", [("tiny_lora", "Aurora", 33, 64, fx.LEVELS4),
-                                                          ("tiny_air", "AuroraAirPollution", 45, 90, fx.LEVELS13)])
+@pytest.mark.parametrize("cfg_name,cls_name,h,w,levels", [
+    ("tiny_lora", "Aurora", 33, 64, fx.LEVELS4),            # 33 rows: cropped on the device, kernels read the copies
+    ("tiny_lora", "Aurora", 32, 64, fx.LEVELS4),            # no crop: kernels read the upload buffers themselves
+    ("tiny_air", "AuroraAirPollution", 48, 90, fx.LEVELS13),  # + previous-state pointers into the upload buffers
+])
 def test_pinned_host_batches_take_the_overlapped_upload_and_give_the_same_bits(cfg_name, cls_name, h, w, levels):
     """Batches in pinned host memory are uploaded on a copy stream into two alternating device buffer sets
     (`AuroraEngine._upload_pinned`); five back-to-back steps on different inputs — no synchronisation in between, so
