@@ -40,20 +40,22 @@ class Metadata:
     rollout_step: int = 0
 
     def __post_init__(self) -> None:
-        if not (torch.all(self.lat <= 90) and torch.all(self.lat >= -90)):
-            raise ValueError("Latitudes must be in the range [-90, 90].")
-        if not (torch.all(self.lon >= 0) and torch.all(self.lon < 360)):
-            raise ValueError("Longitudes must be in the range [0, 360).")
-        if self.lat.dim() == self.lon.dim() == 1:
-            if not torch.all(self.lat[1:] - self.lat[:-1] < 0):
-                raise ValueError("Latitudes must be strictly decreasing.")
-            if not torch.all(self.lon[1:] - self.lon[:-1] > 0):
-                raise ValueError("Longitudes must be strictly increasing.")
-        elif self.lat.dim() == self.lon.dim() == 2:
-            if not torch.all(self.lat[1:, :] - self.lat[:-1, :]):
-                raise ValueError("Latitudes must be strictly decreasing along every column.")
-            if not torch.all(self.lon[:, 1:] - self.lon[:, :-1] > 0):
-                raise ValueError("Longitudes must be strictly increasing along every row.")
+        """Coordinate checks with the reference's messages (`aurora/batch.py:45-68`)."""
+        lat, lon = self.lat, self.lon
+
+        def require(ok: torch.Tensor, message: str) -> None:
+            if not bool(ok):
+                raise ValueError(message)
+
+        require(((lat <= 90) & (lat >= -90)).all(), "Latitudes must be in the range [-90, 90].")
+        require(((lon >= 0) & (lon < 360)).all(), "Longitudes must be in the range [0, 360).")
+        if lat.dim() == 1 and lon.dim() == 1:
+            require((lat.diff() < 0).all(), "Latitudes must be strictly decreasing.")
+            require((lon.diff() > 0).all(), "Longitudes must be strictly increasing.")
+        elif lat.dim() == 2 and lon.dim() == 2:
+            # (the reference only requires non-zero latitude steps for matrix-valued coordinates, batch.py:61)
+            require((lat.diff(dim=0) != 0).all(), "Latitudes must be strictly decreasing along every column.")
+            require((lon.diff(dim=1) > 0).all(), "Longitudes must be strictly increasing along every row.")
         else:
             raise ValueError("The latitudes and longitudes must either both be vectors or both be matrices.")
 
