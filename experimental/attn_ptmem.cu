@@ -11,6 +11,12 @@
 //   * S tile 1 (query rows 128..143) is re-issued after P V, so its P can live in its own S columns;
 //   * (batch, head) of an item travel through the stage metadata: no integer divisions in the epilogue.
 //
+// Expected effect (to be measured): the softmax loop body loses its P-store phase (26 % of the samples) and the
+// epilogue's divisions (~10 %); in exchange the tile-1 warp's chain now contains P V(n) and S1(n+1) (its S tile can
+// only be re-issued after the P V that reads P1 out of the same columns), roughly +700 cycles per item on ITS chain.
+// With ~5 400 cycles per item today that suggests ~4 200 (-20 %).  If the tile-1 chain turns out to be the pole, the
+// next step is to keep P1 in shared memory (2 KB, SS-mode P V for tile 1 only) and issue S1(n+1) early again.
+//
 // Whole-grid, full 144-token windows only (no latitude slabs yet).  Built and compared with the shipped kernel by
 // experimental/probe_attn_x1.py (needs a B200).  It has been compiled for sm_100a but NEVER RUN: round 1 had no
 // GPU time left when it was written.
