@@ -70,3 +70,27 @@ def test_oracle_rollout_matches_reference():
                 assert fx.rel_mean_abs(v, torch.from_numpy(gold[f"step{i}.surf.{k}"])) < 1e-6, (i, k)
             for k, v in pred.atmos_vars.items():
                 assert fx.rel_mean_abs(v, torch.from_numpy(gold[f"step{i}.atmos.{k}"])) < 1e-6, (i, k)
+
+
+def test_oracle_rollout_lora_modes_like_reference_test():
+    """The reference's tests/test_rollout.py on the oracle: identical weights, one model with a single LoRA for every
+    step and one with a separate LoRA per step — the first prediction agrees, later ones do not; time and
+    `rollout_step` advance by one model step each."""
+    from datetime import timedelta
+
+    cfg1, cfg2 = fx.CONFIGS["tiny_lora"], fx.CONFIGS["tiny_lora_all"]
+    sd2 = fx.make_state_dict(cfg2, seed=5)
+    sd1 = {k: v for k, v in sd2.items() if ".loras." not in k or ".loras.0." in k}  # same init, only LoRA 0
+    assert set(sd1) == {k for k, _, _ in __import__("aurora_b200.spec", fromlist=["param_specs"]).param_specs(cfg1)}
+    batch = fx.make_batch(cfg1, 17, 32, levels=fx.LEVELS4, b=1, seed=5)
+    steps = 3
+    with torch.inference_mode():
+        p1 = list(O.rollout(cfg1, sd1, batch, steps=steps))
+        p2 = list(O.rollout(cfg2, sd2, batch, steps=steps))
+    assert len(p1) == len(p2) == steps
+    for i in range(steps):
+        want_time = tuple(t + (i + 1) * timedelta(hours=6) for t in batch.metadata.time)
+        assert p1[i].metadata.time == p2[i].metadata.time == want_time
+        assert p1[i].metadata.rollout_step == p2[i].metadata.rollout_step == i + 1
+        same = np.allclose(p1[i].surf_vars["2t"].numpy(), p2[i].surf_vars["2t"].numpy(), rtol=1e-4)
+        assert same if i == 0 else not same, i
