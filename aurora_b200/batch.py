@@ -1,9 +1,9 @@
 """``Batch`` and ``Metadata``: the data model at the boundary of ``Aurora.forward``.
 
 Same field names, shapes, validation and error behaviour as the reference (`aurora/batch.py:24-190`),
-restricted to the methods on the forward path: ``normalise`` / ``unnormalise`` / ``crop`` / ``to`` /
-``type``.  File I/O and re-gridding (`aurora/batch.py:192-362`) are outside the accelerated path and
-not provided.  On the GPU path normalisation is fused into the patch-embedding loader and
+with the methods on the forward path — ``normalise`` / ``unnormalise`` / ``crop`` / ``to`` / ``type`` — and
+``regrid`` (`aurora/batch.py:192-222, 299-362`).  netCDF file I/O (`aurora/batch.py:224-296`, needs xarray) is
+outside the accelerated path and not provided.  On the GPU path normalisation is fused into the patch-embedding loader and
 un-normalisation into the head's store; the methods here exist for API parity and for callers that
 want the tensors themselves.
 """
@@ -177,8 +177,23 @@ class Batch:
         return self._fmap(lambda x: x.type(t))
 
     # -- outside the accelerated path ---------------------------------------------------------
-    def regrid(self, res: float) -> "Batch":  # pragma: no cover
-        raise NotImplementedError("Batch.regrid (aurora/batch.py:192) is host-side I/O, not part of aurora_b200")
+    def regrid(self, res: float) -> "Batch":
+        """Bilinear re-gridding to a regular `res`-degree grid that includes both poles (`aurora/batch.py:192-222`):
+        `round(180 / res) + 1` latitudes from 90 to -90, `round(360 / res)` longitudes from 0, periodic in longitude,
+        linearly extrapolated in latitude.  Computed in float64 and returned as float32, like the reference, but as
+        one vectorised gather per variable on the tensors' own device instead of a SciPy loop over fields."""
+        n_lat, n_lon = round(180 / res) + 1, round(360 / res)
+        dev = self.metadata.lat.device
+        lat_new = torch.linspace(90, -90, n_lat, dtype=torch.float64, device=dev)
+        lon_new = torch.arange(n_lon, dtype=torch.float64, device=dev) * (360.0 / n_lon)
+        plan = _bilinear_plan(self.metadata.lat, self.metadata.lon, lat_new, lon_new)
+        return Batch(
+            surf_vars={k: _bilinear_apply(v, plan) for k, v in self.surf_vars.items()},
+            static_vars={k: _bilinear_apply(v, plan) for k, v in self.static_vars.items()},
+            atmos_vars={k: _bilinear_apply(v, plan) for k, v in self.atmos_vars.items()},
+            metadata=Metadata(lat=lat_new, lon=lon_new, time=self.metadata.time,
+                              atmos_levels=self.metadata.atmos_levels, rollout_step=self.metadata.rollout_step),
+        )
 
     def to_netcdf(self, path) -> None:  # pragma: no cover
         raise NotImplementedError("netCDF I/O (aurora/batch.py:224) is not part of aurora_b200")
@@ -186,3 +201,35 @@ class Batch:
     @classmethod
     def from_netcdf(cls, path) -> "Batch":  # pragma: no cover
         raise NotImplementedError("netCDF I/O (aurora/batch.py:260) is not part of aurora_b200")
+
+
+def _cell_and_weight(grid: torch.Tensor, new: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    """For every `new` coordinate: index i of the grid cell [grid[i], grid[i+1]] used for it (clamped to the first /
+    last cell, so points outside the grid are extrapolated) and the normalised distance from grid[i].  `grid` is
+    strictly monotonic, in either direction."""
+    if grid[-1] < grid[0]:
+        grid, new = -grid, -new
+    i = (torch.searchsorted(grid, new) - 1).clamp(0, grid.numel() - 2)
+    return i, (new - grid[i]) / (grid[i + 1] - grid[i])
+
+
+def _bilinear_plan(lat, lon, lat_new, lon_new):
+    lat, lon = lat.double(), lon.double()
+    if not bool((lon.diff() > 0).all()):
+        raise AssertionError("Longitudes must be strictly increasing.")
+    n = lon.numel()
+    lon_ext = torch.cat((lon[-1:] - 360, lon, lon[:1] + 360))         # one wrapped column on either side
+    col = torch.cat((torch.tensor([n - 1], device=lon.device), torch.arange(n, device=lon.device),
+                     torch.tensor([0], device=lon.device)))            # extended column -> source column
+    i, wy = _cell_and_weight(lat, lat_new.double())
+    j, wx = _cell_and_weight(lon_ext, lon_new.double())
+    return i, wy[:, None], col[j], col[j + 1], wx[None, :]
+
+
+def _bilinear_apply(v: torch.Tensor, plan) -> torch.Tensor:
+    i, wy, j0, j1, wx = plan
+    v = v.double()
+    top, bot = v[..., i, :], v[..., i + 1, :]
+    out = (top[..., j0] * (1 - wy) * (1 - wx) + top[..., j1] * (1 - wy) * wx
+           + bot[..., j0] * wy * (1 - wx) + bot[..., j1] * wy * wx)
+    return out.float()

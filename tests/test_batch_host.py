@@ -9,7 +9,7 @@ from pathlib import Path
 import pytest
 import torch
 
-from aurora_b200 import Metadata
+from aurora_b200 import Batch, Metadata
 from aurora_b200 import stats
 from tests import fixtures as fx
 
@@ -94,3 +94,48 @@ def test_against_reference_classes_live():
             for k, v in getattr(ref, grp).items():
                 assert torch.equal(getattr(ours, grp)[k], v), (grp, k)
         assert torch.equal(ours.metadata.lat, ref.metadata.lat)
+
+
+def test_regrid_properties():
+    """Bilinear re-gridding (aurora/batch.py:192-222): a field that is linear in latitude and piecewise linear in
+    longitude is reproduced exactly, re-gridding to the same grid is the identity, shapes follow the reference."""
+    cfg = fx.CONFIGS["tiny"]
+    b = fx.make_batch(cfg, 17, 32, levels=fx.LEVELS4)          # 11.25-degree grid including both poles
+    same = b.regrid(11.25)
+    assert same.spatial_shape == (17, 32)
+    for k in b.surf_vars:
+        assert torch.allclose(same.surf_vars[k], b.surf_vars[k], rtol=5e-6, atol=1e-4)
+    fine = b.regrid(5.625)
+    assert fine.spatial_shape == (33, 64) and fine.atmos_vars["t"].shape == (1, 2, 4, 33, 64)
+    assert fine.metadata.lat.dtype == torch.float64 and float(fine.metadata.lat[0]) == 90.0 and float(fine.metadata.lon[-1]) < 360
+    lat, lon = b.metadata.lat.double(), b.metadata.lon.double()
+    ramp = (3.0 * lat[:, None] + 0.0 * lon[None, :]).float()
+    bb = Batch({"2t": ramp[None, None]}, {"z": ramp}, {"t": ramp[None, None, None]}, b.metadata)
+    out = bb.regrid(5.625)
+    want = (3.0 * out.metadata.lat[:, None] + 0.0 * out.metadata.lon[None, :]).float()
+    assert torch.allclose(out.static_vars["z"], want, atol=1e-4)
+    # every second point of the finer grid is an original grid point
+    assert torch.allclose(fine.surf_vars["2t"][..., ::2, ::2], b.surf_vars["2t"], rtol=5e-6, atol=1e-4)
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference checkout not present (GPU box)")
+@pytest.mark.parametrize("res", [5.0, 11.25, 7.3])
+def test_regrid_against_reference_live(res):
+    sys.path[:0] = [str(REF), str(Path(__file__).parent / "_shims")]
+    try:
+        import aurora
+    finally:
+        del sys.path[:2]
+    cfg = fx.CONFIGS["tiny"]
+    b = fx.make_batch(cfg, 17, 32, levels=fx.LEVELS4, b=2)
+    rb = aurora.Batch(dict(b.surf_vars), dict(b.static_vars), dict(b.atmos_vars),
+                      aurora.Metadata(lat=b.metadata.lat, lon=b.metadata.lon, time=b.metadata.time,
+                                      atmos_levels=b.metadata.atmos_levels))
+    ours, ref = b.regrid(res), rb.regrid(res)
+    assert ours.spatial_shape == tuple(ref.spatial_shape)
+    assert torch.allclose(ours.metadata.lat, ref.metadata.lat, atol=1e-12) and torch.allclose(ours.metadata.lon, ref.metadata.lon, atol=1e-12)
+    for grp in ("surf_vars", "static_vars", "atmos_vars"):
+        for k, v in getattr(ref, grp).items():
+            got = getattr(ours, grp)[k]
+            assert got.dtype == torch.float32 and got.shape == v.shape
+            assert torch.allclose(got, v, rtol=2e-6, atol=1e-6 * float(v.abs().max())), (grp, k, float((got - v).abs().max()))
