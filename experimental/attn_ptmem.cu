@@ -1,6 +1,6 @@
 // EXPERIMENTAL — round-2 staging area, NOT part of libaurora_b200.so and not on any product path.
 //
-// Variant "x1" of the tcgen05 / TMEM window-attention kernel, written against the findings of
+// Variants "x1" / "x1b" of the tcgen05 / TMEM window-attention kernel, written against the findings of
 // profiles/r01p_ncu_final_captures.md (the softmax warps are the per-item critical path; 26 % of their time is the
 // P -> shared-memory store + proxy fence, 16 % is waiting for gathered tiles, ~10 % is item re-decoding in the epilogue):
 //
@@ -33,25 +33,34 @@ namespace ab {
 namespace x1 {
 using namespace tc;
 
-constexpr int kStagesX = 4;                                   // 4 x 54 KB q/k/v ring
-constexpr int kOffMetaX = kStagesX * kStageBytes;             // 216 KB
+// Two variants of the same kernel:
+//   <4, false>  "x1" : P of BOTH tiles in TMEM; four q/k/v stages; S tile 1 re-issued after P V (its P overwrites it)
+//   <3, true>   "x1b": P of tile 0 in TMEM, P of tile 1 (16 live rows, 6 KB) through shared memory as in the shipped
+//                      kernel, so S tile 1 is issued early again; three stages (the 4th does not fit next to P1)
+constexpr int kMaxStagesX = 4;
 constexpr int kMetaBytesX = 6144;
-constexpr int kSmemBytesX = kOffMetaX + kMetaBytesX + 1024;   // 223 KB (limit 227 KB)
+constexpr int kP1AreaBytes = 3 * kP1BlockBytes;               // 6 KB
+template <int kSt, bool kP1Smem>
+struct Lay {
+  static constexpr int kOffP1 = kSt * kStageBytes;            // only used when kP1Smem
+  static constexpr int kOffMeta = kOffP1 + (kP1Smem ? kP1AreaBytes : 0);
+  static constexpr int kSmem = kOffMeta + kMetaBytesX + 1024;
+  static_assert(kSmem <= 227 * 1024, "shared memory");
+};
 // TMEM columns (all multiples of 16): S0 [0,144)  P0 [144,216)  O0 [224,288)  S1 [288,432) with P1 = [288,360)  O1 [432,496)
 constexpr uint32_t kColS0 = 0, kColP0 = 144, kColO0 = 224, kColS1 = 288, kColP1 = kColS1, kColO1 = 432;
 
 struct MetaX {
-  int lsrc[kStagesX][kTok];
-  int src[kStagesX][kTok];
-  alignas(16) uint8_t grp[kStagesX][kTok + 16];
-  int masked[kStagesX];
-  int head[kStagesX];
-  int batch[kStagesX];
-  uint64_t full[kStagesX], empty[kStagesX], s0_full, s1_full, s0_free, p_full, o_full, o_free;
+  int lsrc[kMaxStagesX][kTok];
+  int src[kMaxStagesX][kTok];
+  alignas(16) uint8_t grp[kMaxStagesX][kTok + 16];
+  int masked[kMaxStagesX];
+  int head[kMaxStagesX];
+  int batch[kMaxStagesX];
+  uint64_t full[kMaxStagesX], empty[kMaxStagesX], s0_full, s1_full, s0_free, p_full, o_full, o_free;
   uint32_t tmem_slot;
 };
 static_assert(sizeof(MetaX) <= kMetaBytesX, "meta area");
-static_assert(kSmemBytesX <= 227 * 1024, "shared memory");
 
 // D[tmem] (+)= A[tmem] * B[smem]^T : A = 128 lanes x 8 columns of packed 16-bit pairs (K = 16) per instruction.
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
@@ -85,6 +94,7 @@ __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+template <int kStagesX, bool kP1Smem>
 __global__ void __launch_bounds__(kThreads, 1)
 window_attention_x1_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_halo,
                            const AttnArgs a) {
@@ -92,7 +102,7 @@ window_attention_x1_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
   // rows 0..127); differences are marked X1.
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  MetaX* meta = reinterpret_cast<MetaX*>(smem + kOffMetaX);
+  MetaX* meta = reinterpret_cast<MetaX*>(smem + Lay<kStagesX, kP1Smem>::kOffMeta);
   const WinGeom& g = a.g;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -110,7 +120,9 @@ window_attention_x1_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
     }
     mbar_init(&meta->s0_full, 1);
     mbar_init(&meta->s1_full, 1);
-    mbar_init(&meta->s0_free, 4);  // X1: only the four tile-0 warps release S0; S1 is re-issued after P V in pipe order
+    // X1: only the four tile-0 warps release S0 (S1 is re-issued after P V in pipe order); X1b: all five warps release
+    // both S tiles, as in the shipped kernel
+    mbar_init(&meta->s0_free, kP1Smem ? 5 : 4);
     mbar_init(&meta->p_full, 5);
     mbar_init(&meta->o_full, 1);
     mbar_init(&meta->o_free, 5);
@@ -249,20 +261,30 @@ window_attention_x1_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
           mbar_wait(&meta->s0_free, n & 1);  // the tile-0 softmax warps have pulled S0(n) out of TMEM
           tc_fence_after_sync();
           issue_s0(n + 1);
+          if constexpr (kP1Smem) issue_s1(n + 1);  // X1b: P1 is in shared memory, S1 may be overwritten right away
         }
         mbar_wait(&meta->p_full, n & 1);     // P(n) is in TMEM (tcgen05.st + wait::st + fence on the writer side)
         if (n > 0) mbar_wait(&meta->o_free, (n - 1) & 1);
         tc_fence_after_sync();
         const uint32_t va = smem_u32(smem + (n % kStagesX) * kStageBytes) + 2 * kTileBytes;
+        // X1b: tile-1 A operand from shared memory; it starts 96 rows before its 16 live rows (don't-care rows that
+        // fall into the last stage's V tile: mapped memory, accumulator rows never read), as in the shipped kernel
+        const uint32_t p1 = smem_u32(smem + Lay<kStagesX, kP1Smem>::kOffP1) - kP1Rewind;
 #pragma unroll
         for (int j = 0; j < kTok / 16; ++j) {  // 9 k-steps of 16 keys = 8 TMEM columns of packed bf16 pairs each
           const uint64_t dv = umma_desc_k_sw128(va + j * 16 * kRowBytes);
           umma_bf16_ts(tmem_base + kColO0, tmem_base + kColP0 + j * 8, dv, idesc_o, j != 0);
-          umma_bf16_ts(tmem_base + kColO1, tmem_base + kColP1 + j * 8, dv, idesc_o, j != 0);
+          if constexpr (kP1Smem)
+            umma_bf16_ss(tmem_base + kColO1, umma_desc_k_sw128(p1 + (j >> 2) * kP1BlockBytes + (j & 3) * 32), dv, idesc_o,
+                         j != 0);
+          else
+            umma_bf16_ts(tmem_base + kColO1, tmem_base + kColP1 + j * 8, dv, idesc_o, j != 0);
         }
         umma_commit(&meta->o_full);
         umma_commit(&meta->empty[n % kStagesX]);  // q / k / v of this stage are consumed
-        if (n + 1 < cnt) issue_s1(n + 1);        // overwrites P1(n) only after P V(n) above has read it
+        if constexpr (!kP1Smem) {
+          if (n + 1 < cnt) issue_s1(n + 1);      // overwrites P1(n) only after P V(n) above has read it
+        }
       }
     }
   } else {
@@ -347,7 +369,7 @@ window_attention_x1_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
       }
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0 && tile == 0) mbar_arrive(&meta->s0_free);  // S0(n) is in registers: S0(n+1) may overwrite it
+      if (lane == 0 && (tile == 0 || kP1Smem)) mbar_arrive(&meta->s0_free);  // S(n) is in registers: S(n+1) may overwrite it
       if (masked) {
         // 0 / -100 on the scaled logits == 0 / -800 on the raw q.k products (scale 1/8)
         const uint4* g16 = reinterpret_cast<const uint4*>(meta->grp[st]);
@@ -388,7 +410,20 @@ window_attention_x1_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
       // X1: P(n) -> TMEM.  tcgen05.st is warp-collective: every lane stores (rows >= 144 hold don't-care values whose
       // accumulator rows are never read).  P0(n) may replace P0(n-1) because epilogue(n-1) above has waited for
       // o_full(n-1), i.e. P V(n-1) has retired; P1(n) goes over S1(n), which this thread has already pulled out.
-      {
+      if (kP1Smem && tile) {
+        // X1b, tile 1: 16 live rows to K-major swizzled shared memory (three 2 KB blocks of 64 keys), generic -> async
+        // proxy fence, exactly the shipped path
+        const uint32_t prow = smem_u32(smem + Lay<kStagesX, kP1Smem>::kOffP1) + (lrow - 96) * kRowBytes;
+#pragma unroll
+        for (int ch = 0; ch < kTok / 8; ++ch) {
+          const uint32_t addr = prow + (ch >> 3) * kP1BlockBytes + (((ch & 7) ^ (lrow & 7)) << 4);
+          if (valid)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * ch]), "r"(pk[4 * ch + 1]),
+                         "r"(pk[4 * ch + 2]), "r"(pk[4 * ch + 3])
+                         : "memory");
+        }
+        fence_proxy_async_smem();
+      } else {
         uint32_t c0[32], c1[32], c2[8];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -446,15 +481,17 @@ extern "C" int ab_window_attention_x1(const AbWindowAttention* p, void* stream) 
   a.num_heads = p->num_heads;
   a.dim = p->num_heads * kHeadDim;
   a.tokens_per_batch = static_cast<long long>(p->res[0]) * p->res[1] * p->res[2];
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(x1::window_attention_x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         x1::kSmemBytesX);
+  // AB_X1_VARIANT=b selects the "x1b" kernel (P of tile 1 through shared memory, three stages)
+  const char* var = getenv("AB_X1_VARIANT");
+  const bool vb = var != nullptr && var[0] == 'b';
+  auto kern = vb ? x1::window_attention_x1_kernel<3, true> : x1::window_attention_x1_kernel<4, false>;
+  const int smem_bytes = vb ? x1::Lay<3, true>::kSmem : x1::Lay<4, false>::kSmem;
+  {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) {
       set_error("ab_window_attention_x1: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return AB_ERR_CUDA;
     }
-    attr_set = true;
   }
   // largest run length R such that every run of R in-window tokens along W is all padding or contiguous (as shipped)
   auto gcd = [](int x, int y) { while (y) { int t = x % y; x = y; y = t; } return x; };
@@ -477,7 +514,7 @@ extern "C" int ab_window_attention_x1(const AbWindowAttention* p, void* stream) 
   if (make_tmap_16bit_2d(&tq, p->qkv, rows, 3ll * a.dim, 3ll * a.dim, r, kHeadDim, false) == AB_OK) a.box_rows = r;
   const long long items = static_cast<long long>(p->batch) * a.g.nwindows * p->num_heads;
   const unsigned grid = static_cast<unsigned>(items < sm_count() ? items : sm_count());
-  x1::window_attention_x1_kernel<<<grid, tc::kThreads, x1::kSmemBytesX, reinterpret_cast<cudaStream_t>(stream)>>>(tq, th, a);
+  kern<<<grid, tc::kThreads, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(tq, th, a);
   AB_COUNT_LAUNCH(1);
   AB_CHECK_LAUNCH("ab_window_attention_x1");
   return AB_OK;

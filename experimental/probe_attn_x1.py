@@ -63,13 +63,7 @@ def main() -> None:
                 if rc != 0:
                     raise RuntimeError(x1.ab_last_error().decode())
 
-            launch()
-            torch.cuda.synchronize()
-            diff = (out.float() - ref.float()).abs()
-            rec = {"stage": name, "shifted": shifted, "max_abs_diff": float(diff.max()), "nan": int(torch.isnan(out).sum()),
-                   "equal": bool(torch.equal(out, ref))}
-            for fn, key in ((launch, "x1_ms"), (lambda: cabi.window_attention(
-                    qkv, ref, batch=1, res=res, window=ws, shift=ss, num_heads=heads, pad_qkv=pad), "shipped_ms")):
+            def timed(fn):
                 for _ in range(3):
                     fn()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -78,7 +72,19 @@ def main() -> None:
                     fn()
                 e1.record()
                 torch.cuda.synchronize()
-                rec[key] = round(e0.elapsed_time(e1) / 10, 4)
+                return round(e0.elapsed_time(e1) / 10, 4)
+
+            rec = {"stage": name, "shifted": shifted}
+            for variant in ("a", "b"):       # a = x1 (both P tiles in TMEM, 4 stages), b = x1b (P1 via smem, 3 stages)
+                os.environ["AB_X1_VARIANT"] = variant
+                out.fill_(float("nan"))
+                launch()
+                torch.cuda.synchronize()
+                diff = (out.float() - ref.float()).abs()
+                rec[f"x1{variant}"] = {"max_abs_diff": float(diff.max()), "nan": int(torch.isnan(out).sum()),
+                                       "equal": bool(torch.equal(out, ref)), "ms": timed(launch)}
+            rec["shipped_ms"] = timed(lambda: cabi.window_attention(
+                qkv, ref, batch=1, res=res, window=ws, shift=ss, num_heads=heads, pad_qkv=pad))
             print(json.dumps(rec), flush=True)
 
 
