@@ -2,8 +2,8 @@
 
 Same field names, shapes, validation and error behaviour as the reference (`aurora/batch.py:24-190`),
 with the methods on the forward path — ``normalise`` / ``unnormalise`` / ``crop`` / ``to`` / ``type`` — and
-``regrid`` (`aurora/batch.py:192-222, 299-362`).  netCDF file I/O (`aurora/batch.py:224-296`, needs xarray) is
-outside the accelerated path and not provided.  On the GPU path normalisation is fused into the patch-embedding loader and
+``regrid`` (`aurora/batch.py:192-222, 299-362`) and netCDF I/O in the reference's file layout
+(`aurora/batch.py:224-296`; needs xarray + netCDF4, raises the reference's error without them).  On the GPU path normalisation is fused into the patch-embedding loader and
 un-normalisation into the head's store; the methods here exist for API parity and for callers that
 want the tensors themselves.
 """
@@ -195,12 +195,46 @@ class Batch:
                               atmos_levels=self.metadata.atmos_levels, rollout_step=self.metadata.rollout_step),
         )
 
-    def to_netcdf(self, path) -> None:  # pragma: no cover
-        raise NotImplementedError("netCDF I/O (aurora/batch.py:224) is not part of aurora_b200")
+    # -- file I/O in the reference's layout (`aurora/batch.py:224-296`); needs xarray + netCDF4 like the reference ----
+    _NC_DIMS = {"surf": ("batch", "history", "latitude", "longitude"), "static": ("latitude", "longitude"),
+                "atmos": ("batch", "history", "level", "latitude", "longitude")}
+
+    @staticmethod
+    def _xarray():
+        try:
+            import xarray
+        except ImportError as e:
+            raise RuntimeError("`xarray` must be installed.") from e
+        return xarray
+
+    def to_netcdf(self, path) -> None:
+        """One data variable per field, named `surf_<name>` / `static_<name>` / `atmos_<name>`, coordinates
+        latitude / longitude / time / level / rollout_step."""
+        xr = self._xarray()
+        groups = {"surf": self.surf_vars, "static": self.static_vars, "atmos": self.atmos_vars}
+        data = {f"{grp}_{name}": (self._NC_DIMS[grp], t.detach().cpu().numpy())
+                for grp, fields in groups.items() for name, t in fields.items()}
+        md = self.metadata
+        coords = {"latitude": md.lat.detach().cpu().numpy(), "longitude": md.lon.detach().cpu().numpy(),
+                  "time": list(md.time), "level": list(md.atmos_levels), "rollout_step": md.rollout_step}
+        xr.Dataset(data, coords=coords).to_netcdf(path)
 
     @classmethod
-    def from_netcdf(cls, path) -> "Batch":  # pragma: no cover
-        raise NotImplementedError("netCDF I/O (aurora/batch.py:260) is not part of aurora_b200")
+    def from_netcdf(cls, path) -> "Batch":
+        xr = cls._xarray()
+        ds = xr.load_dataset(path, engine="netcdf4")
+        fields: dict[str, dict[str, torch.Tensor]] = {"surf": {}, "static": {}, "atmos": {}}
+        for key in ds:
+            grp, _, name = str(key).partition("_")
+            if grp in fields:
+                fields[grp][name] = torch.from_numpy(ds[key].values)
+        return cls(
+            surf_vars=fields["surf"], static_vars=fields["static"], atmos_vars=fields["atmos"],
+            metadata=Metadata(
+                lat=torch.from_numpy(ds.latitude.values), lon=torch.from_numpy(ds.longitude.values),
+                time=tuple(ds.time.values.astype("datetime64[s]").tolist()), atmos_levels=tuple(ds.level.values),
+                rollout_step=int(ds.rollout_step.values)),
+        )
 
 
 def _cell_and_weight(grid: torch.Tensor, new: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:

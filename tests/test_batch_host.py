@@ -139,3 +139,21 @@ def test_regrid_against_reference_live(res):
             got = getattr(ours, grp)[k]
             assert got.dtype == torch.float32 and got.shape == v.shape
             assert torch.allclose(got, v, rtol=2e-6, atol=1e-6 * float(v.abs().max())), (grp, k, float((got - v).abs().max()))
+
+
+def test_netcdf_io_needs_xarray_like_the_reference(tmp_path):
+    try:
+        import xarray  # noqa: F401
+    except ImportError:
+        b = fx.make_batch(fx.CONFIGS["tiny"], 16, 32, levels=fx.LEVELS4)
+        with pytest.raises(RuntimeError, match="`xarray` must be installed"):
+            b.to_netcdf(tmp_path / "b.nc")
+        with pytest.raises(RuntimeError, match="`xarray` must be installed"):
+            Batch.from_netcdf(tmp_path / "b.nc")
+        return
+    b = fx.make_batch(fx.CONFIGS["tiny"], 16, 32, levels=fx.LEVELS4)   # round trip when the libraries are there
+    b.to_netcdf(tmp_path / "b.nc")
+    r = Batch.from_netcdf(tmp_path / "b.nc")
+    for k in b.surf_vars:
+        assert torch.equal(r.surf_vars[k], b.surf_vars[k])
+    assert r.metadata.time == b.metadata.time and tuple(r.metadata.atmos_levels) == tuple(b.metadata.atmos_levels)
