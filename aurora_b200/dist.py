@@ -1,7 +1,7 @@
 """Multi-GPU plumbing for replica runs: one process per GPU, `torch.distributed` for rendezvous and for
 the only cross-rank operations the forward path needs today — a barrier and a max-reduction of device
-timings.  Independent forecasts need no data-path collective; latitude sharding of a
-single forecast (halo exchange per shifted stage) is designed there and not implemented yet."""
+timings.  Independent forecasts need no data-path collective; the latitude sharding of a
+single forecast and its halo exchange live in `aurora_b200/sharding.py`."""
 
 from __future__ import annotations
 
