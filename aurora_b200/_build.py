@@ -8,6 +8,7 @@ imports torch: the library has a pure C ABI (``include/aurora_b200.h``).
 from __future__ import annotations
 
 import concurrent.futures
+import hashlib
 import os
 import shutil
 import subprocess
@@ -41,14 +42,29 @@ def sources() -> list[Path]:
     return sorted(CSRC.glob("*.cu"))
 
 
-def _deps_mtime() -> float:
+HASH_PATH = CSRC / "libaurora_b200.srchash"  # git-ignored like the .so; travels with a snapshot
+
+
+def _dep_files() -> list[Path]:
     files = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h"))
     files += list((ROOT / "include").glob("*.h"))
-    return max(f.stat().st_mtime for f in files)
+    return sorted(files)
+
+
+def source_hash() -> str:
+    """SHA-256 over every source / header the library is built from (and the compiler flags).  Content, not mtime:
+    a snapshot copied to another machine keeps its library fresh whatever the copy did to the time stamps."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in _dep_files():
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()
 
 
 def is_stale() -> bool:
-    return (not LIB_PATH.exists()) or LIB_PATH.stat().st_mtime < _deps_mtime()
+    if not LIB_PATH.exists() or not HASH_PATH.exists():
+        return True
+    return HASH_PATH.read_text().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> Path:
@@ -57,12 +73,11 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
         return LIB_PATH
     nvcc = _nvcc()
     OBJ_DIR.mkdir(parents=True, exist_ok=True)
-    dep_m = _deps_mtime()
+    digest = source_hash()
     headers_m = max(
         [f.stat().st_mtime for f in list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h"))]
         + [f.stat().st_mtime for f in (ROOT / "include").glob("*.h")]
     )
-    del dep_m
 
     def compile_one(src: Path) -> tuple[Path, str]:
         obj = OBJ_DIR / (src.stem + ".o")
@@ -90,6 +105,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     os.replace(tmp, LIB_PATH)
+    HASH_PATH.write_text(digest + "\n")
     return LIB_PATH
 
 

@@ -20,6 +20,7 @@ __all__ = [
     "linear_small", "patchify", "unpatchify", "AbFieldIn", "AbFieldOut",
 ]
 
+ABI_VERSION = 2  # == AB_ABI_VERSION in include/aurora_b200.h
 AB_ACT_NONE = 0
 AB_ACT_GELU_ERF = 1
 
@@ -69,10 +70,11 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is None:
         path = _build.LIB_PATH
-        if not path.exists():
-            _build.build()
+        _build.build()  # no-op when the library matches the sources (content hash); never load a stale binary
         handle = C.CDLL(str(path))
         handle.ab_version.restype = C.c_int
+        if handle.ab_version() != ABI_VERSION:
+            raise AbError(f"libaurora_b200.so has ABI version {handle.ab_version()}, this binding expects {ABI_VERSION}")
         handle.ab_last_error.restype = C.c_char_p
         handle.ab_launch_count.restype = C.c_ulonglong
         for name in EXPORTS:

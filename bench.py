@@ -181,124 +181,200 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline (oracle port) — bounded sample
+# Reference legs: the UNMODIFIED reference (oracle/_ref, see oracle/build_ref.py) on the host cores and on the GPU
 # ------------------------------------------------------------------------------------------------
-_THREADS: dict = {}
+CPU_THREADS_CAP = 32  # PyTorch's CPU kernels stop scaling on many-core hosts (128 threads measured 2.8x SLOWER than 32)
+SAMPLE_LAT_DIV = 3    # the bounded sample keeps the first 1/3 of the latitude rows of every U-Net stage (fixed)
 
 
-def pick_threads(workload: str, cores: int) -> int:
-    """Host threads for the CPU legs: the fastest of {cores, cores/2, cores/4} on a small slice of the sample
-    (PyTorch's CPU kernels do not always scale to every hardware thread of a large box)."""
-    if workload not in _THREADS:
-        best = None
-        for n in sorted({max(1, cores), max(1, cores // 2), max(1, cores // 4)}, reverse=True):
-            t = cpu_baseline_sample(workload, n, lat_fraction=6, calibrate=True)["sample_seconds"]
-            if best is None or t < best[0]:
-                best = (t, n)
-        _THREADS[workload] = best[1]
-    return _THREADS[workload]
+def host_threads() -> int:
+    return max(1, min(CPU_THREADS_CAP, os.cpu_count() or 1))
 
 
-def cpu_baseline_sample(workload: str, cores: int, lat_fraction: int = 1, calibrate: bool = False) -> dict:
-    """Time the CPU oracle on a bounded sample of the workload and extrapolate by algorithmic FLOPs.
+def build_reference(workload: str, device: str, autocast: bool, seed: int = 0):
+    """The unmodified reference model of this workload with the same random parameters the `ours` arm uses."""
+    from oracle import ref
 
-    Sample: one Swin3D block of every U-Net stage (unshifted for stage 1, shifted for stages 2-3) at the
-    workload's real widths and token grid, fp32, `cores` host threads; `lat_fraction` > 1 keeps only the first
-    1 / lat_fraction of the latitude rows of every stage (whole window rows) to bound the sample further.
-    Blocks are ~84 % of the step's FLOPs and cost the same ~1.7 TFLOP at every stage; the step time is the
-    sample time scaled by (total step FLOPs / sample FLOPs)."""
+    cls, h, w, levels = WORKLOADS[workload]
+    model = ref.build_model(cls, device=device, autocast=autocast)
+    randomise_parameters_(model, seed=seed)
+    return model
+
+
+def reference_sample_fn(model, workload: str):
+    """One bounded-sample "step" of the reference's CPU path: the reference's OWN modules with their own weights —
+    the second (shifted-window) Swin3DTransformerBlock of every encoder stage on the first 1/SAMPLE_LAT_DIV of the
+    stage's latitude rows (whole window rows), plus the Perceiver decoder's MLP on the same fraction of its rows.
+    The sample is the same whatever --steps is."""
+    cls, h, w, levels = WORKLOADS[workload]
+    p = model.patch_size
+    res0 = (4, (h - h % p) // p, w // p)
+    g = torch.Generator().manual_seed(0)
+    dev = next(model.parameters()).device
+    c = torch.randn(1, model.backbone.time_mlp[0].in_features, generator=g).to(dev)
+    items = []
+    res = res0
+    for i, layer in enumerate(model.backbone.encoder_layers):
+        blk = layer.blocks[min(1, len(layer.blocks) - 1)]
+        wh = blk.window_size[1]
+        rows = max(wh, (res[1] // SAMPLE_LAT_DIV + wh - 1) // wh * wh) if res[1] > wh else res[1]
+        r = (res[0], min(rows, res[1]), res[2])
+        x = torch.randn(1, r[0] * r[1] * r[2], blk.dim, generator=g).to(dev)
+        items.append((blk, x, r))
+        res = (res[0], (res[1] + res[1] % 2) // 2, (res[2] + res[2] % 2) // 2)
+    mlp = model.decoder.level_decoder.layers[0][1]
+    e = mlp.net[0].in_features
+    rows = max(1024, len(levels) * res0[1] * res0[2] // (4 * SAMPLE_LAT_DIV))
+    xm = torch.randn(1, rows, e, generator=g).to(dev)
+
+    def step() -> float:
+        t0 = time.perf_counter()
+        with torch.inference_mode():
+            for blk, x, r in items:
+                blk(x, c, r, rollout_step=0)
+            mlp(xm)
+        return time.perf_counter() - t0
+
+    desc = ("reference modules on a bounded sample: shifted Swin3DTransformerBlock of every encoder stage on "
+            + ", ".join(f"{r}" for _, _, r in items) + f" tokens + Perceiver-decoder MLP on {rows} rows, fp32")
+    return step, desc
+
+
+def reference_cpu_measure(workload: str, n_warm: int, n_timed: int) -> dict:
+    """The reference's CPU path on this box's host cores: ONE complete `Aurora.forward` of the real reference on the
+    workload (timed, after the samples have warmed oneDNN up), and `n_timed` bounded-sample steps.  The samples are
+    scaled to whole steps by the factor measured in this very run (complete forward / median sample), not by FLOPs."""
+    from oracle import ref
+
+    threads = host_threads()
+    torch.set_num_threads(threads)
+    cls, h, w, levels = WORKLOADS[workload]
+    model = build_reference(workload, "cpu", autocast=False)
+    step, desc = reference_sample_fn(model, workload)
+    for _ in range(max(1, n_warm)):
+        step()
+    batch = ref.to_ref_batch(make_host_batch(_our_config(workload), h, w, levels, pinned=False))
+    t0 = time.perf_counter()
+    with torch.inference_mode():
+        model.forward(batch)
+    t_full = time.perf_counter() - t0
+    del batch
+    times = [step() for _ in range(max(1, n_timed))]
+    med = statistics.median(times)
+    scale = t_full / med
+    return {
+        "value": len(times) / (sum(times) * scale), "unit": "forecast-steps/s", "cores": threads, "kind": "reference",
+        "complete_forward_seconds": t_full, "sample_seconds_median": med, "sample_seconds_min": min(times),
+        "sample_seconds_max": max(times), "samples": len(times), "sample_scale": scale,
+        "sample": f"unmodified reference (oracle/_ref) {cls}, fp32, {threads} host threads of {os.cpu_count()}: one COMPLETE "
+                  f"forward on the {h}x{w}x{len(levels)}L batch = {t_full:.1f} s; steps = {desc}; each sample "
+                  f"({med:.2f} s median) is scaled to a whole step by the factor complete/median = {scale:.1f} measured in "
+                  f"this run",
+        "_times": times,
+    }
+
+
+def port_cpu_measure(workload: str, n_timed: int) -> dict:
+    """Fallback when oracle/_ref did not travel: the oracle PORT (oracle/aurora_oracle.py) on the same fixed sample
+    geometry, scaled to a step by algorithmic FLOPs (no complete forward: kind "port")."""
     from oracle import aurora_oracle as O
     import aurora_b200 as ab
 
+    threads = host_threads()
+    torch.set_num_threads(threads)
     cls, h, w, levels = WORKLOADS[workload]
-    model_cfg = getattr(ab, cls)(_init="empty").config
-    if not calibrate:
-        cores = pick_threads(workload, cores)
-    torch.set_num_threads(cores)
-    p = model_cfg.patch_size
-    res0 = (model_cfg.latent_levels, (h - h % p) // p, w // p)
-    all_res, _ = O.encoder_specs(res0, len(model_cfg.encoder_depths))
+    cfg = getattr(ab, cls)(_init="empty").config
+    cfg = type(cfg)(**{**cfg.__dict__, "use_lora": False})
+    p = cfg.patch_size
+    res = (cfg.latent_levels, (h - h % p) // p, w // p)
     g = torch.Generator().manual_seed(0)
-    sample_flops, t_total, parts = 0.0, 0.0, []
-    c = torch.randn(1, model_cfg.embed_dim, generator=g)
-    for i, res in enumerate(all_res):
-        if lat_fraction > 1:
-            wh = model_cfg.window_size[1]
-            res = (res[0], max(wh, (res[1] // lat_fraction) // wh * wh), res[2])
-        d = model_cfg.embed_dim * 2**i
-        heads = model_cfg.encoder_num_heads[i]
-        l = res[0] * res[1] * res[2]
-        pre = "blk"
-        sd = {
-            f"{pre}.norm1.ln_modulation.1.weight": torch.randn(2 * d, model_cfg.embed_dim, generator=g) * 0.02,
-            f"{pre}.norm1.ln_modulation.1.bias": torch.randn(2 * d, generator=g) * 0.1,
-            f"{pre}.norm2.ln_modulation.1.weight": torch.randn(2 * d, model_cfg.embed_dim, generator=g) * 0.02,
-            f"{pre}.norm2.ln_modulation.1.bias": torch.randn(2 * d, generator=g) * 0.1,
-            f"{pre}.attn.qkv.weight": torch.randn(3 * d, d, generator=g) * 0.02,
-            f"{pre}.attn.qkv.bias": torch.randn(3 * d, generator=g) * 0.02,
-            f"{pre}.attn.proj.weight": torch.randn(d, d, generator=g) * 0.02,
-            f"{pre}.attn.proj.bias": torch.randn(d, generator=g) * 0.02,
-            f"{pre}.mlp.fc1.weight": torch.randn(4 * d, d, generator=g) * 0.02,
-            f"{pre}.mlp.fc1.bias": torch.randn(4 * d, generator=g) * 0.02,
-            f"{pre}.mlp.fc2.weight": torch.randn(d, 4 * d, generator=g) * 0.02,
-            f"{pre}.mlp.fc2.bias": torch.randn(d, generator=g) * 0.02,
-        }
-        # (non-zero biases like any trained checkpoint: with zero biases the zero-padded tokens of shifted windows
-        # produce denormal attention outputs, which slow the CPU GEMMs down several-fold)
-        x = torch.randn(1, l, d, generator=g)
-        cfg_nolora = type(model_cfg)(**{**model_cfg.__dict__, "use_lora": False})
-        with torch.inference_mode():
-            # a forward pass runs 12-20 blocks per stage: per-geometry setup (window map, shift mask, oneDNN primitive
-            # creation) is paid once per stage there, so one untimed pass comes first and the warm pass is timed
-            if not calibrate:
-                O.swin_block(sd, pre, x, c, res, heads, i > 0, cfg_nolora, 0)
-            t0 = time.perf_counter()
-            O.swin_block(sd, pre, x, c, res, heads, i > 0, cfg_nolora, 0)
-            dt = time.perf_counter() - t0
-        nwin = 1
-        ws, _ = O.W.adjust_windows(model_cfg.window_size, (0, 0, 0), res)
-        pads = O.W.pad_lo_hi(res, ws)
-        lp = 1
-        for a in range(3):
-            lp *= res[a] + pads[a][0] + pads[a][1]
-        ntok = ws[0] * ws[1] * ws[2]
-        flops = 2.0 * lp * d * 4 * d + 4.0 * (lp // ntok) * heads * ntok * ntok * 64 + 2.0 * l * d * 8 * d
-        sample_flops += flops
-        t_total += dt
-        parts.append(f"stage{i + 1} {res} D={d}: {dt:.2f}s")
-        del x, sd
-    # The Perceiver encoder / decoder around the backbone are plain per-location MLP GEMMs (SURVEY App. B: 14 % of the
-    # step's FLOPs at 0.25 degree) and run much closer to the CPU's GEMM peak than a Swin block does: sample them
-    # separately (a slice of the decoder's Linear-GELU-Linear at its real widths) and extrapolate each part by its own
-    # FLOPs.  Share of the blocks incl. patch merge / split (SURVEY 8d): 82.86 of 96.8 TFLOP at cfg-Q; other
-    # workloads use the same split.
-    e = 2 * model_cfg.embed_dim
-    hid = int(e * model_cfg.dec_mlp_ratio)
-    rows = max(1024, (13 * res0[1] * res0[2]) // (16 * lat_fraction))
-    msd = {"mlp.0.weight": torch.randn(hid, e, generator=g) * 0.02, "mlp.0.bias": torch.randn(hid, generator=g) * 0.02,
-           "mlp.2.weight": torch.randn(e, hid, generator=g) * 0.02, "mlp.2.bias": torch.randn(e, generator=g) * 0.02}
-    xm = torch.randn(1, rows, e, generator=g)
-    with torch.inference_mode():
-        if not calibrate:
-            O._mlp(msd, "mlp", xm)
+    c = torch.randn(1, cfg.embed_dim, generator=g)
+    items, flops = [], 0.0
+    for i in range(len(cfg.encoder_depths)):
+        wh = cfg.window_size[1]
+        r = (res[0], min(res[1], max(wh, (res[1] // SAMPLE_LAT_DIV + wh - 1) // wh * wh)), res[2])
+        d, heads = cfg.embed_dim * 2**i, cfg.encoder_num_heads[i]
+        sd = {"blk." + k: v for k, v in {
+            "norm1.ln_modulation.1.weight": torch.randn(2 * d, cfg.embed_dim, generator=g) * 0.02,
+            "norm1.ln_modulation.1.bias": torch.randn(2 * d, generator=g) * 0.1,
+            "norm2.ln_modulation.1.weight": torch.randn(2 * d, cfg.embed_dim, generator=g) * 0.02,
+            "norm2.ln_modulation.1.bias": torch.randn(2 * d, generator=g) * 0.1,
+            "attn.qkv.weight": torch.randn(3 * d, d, generator=g) * 0.02, "attn.qkv.bias": torch.randn(3 * d, generator=g) * 0.02,
+            "attn.proj.weight": torch.randn(d, d, generator=g) * 0.02, "attn.proj.bias": torch.randn(d, generator=g) * 0.02,
+            "mlp.fc1.weight": torch.randn(4 * d, d, generator=g) * 0.02, "mlp.fc1.bias": torch.randn(4 * d, generator=g) * 0.02,
+            "mlp.fc2.weight": torch.randn(d, 4 * d, generator=g) * 0.02, "mlp.fc2.bias": torch.randn(d, generator=g) * 0.02,
+        }.items()}
+        l = r[0] * r[1] * r[2]
+        items.append((sd, torch.randn(1, l, d, generator=g), r, heads))
+        flops += 24.0 * l * d * d + 4.0 * l * 144 * d
+        res = (res[0], (res[1] + res[1] % 2) // 2, (res[2] + res[2] % 2) // 2)
+
+    def step():
         t0 = time.perf_counter()
-        O._mlp(msd, "mlp", xm)
-        t_mlp = time.perf_counter() - t0
-    mlp_flops = 4.0 * rows * e * hid
-    parts.append(f"decoder MLP slice {rows}x{e}->{hid}->{e}: {t_mlp:.2f}s")
-    step_flops = ALGO_TFLOP[workload] * 1e12
-    block_share = 82.86 / 96.8
-    est_step_s = (t_total * block_share * step_flops / sample_flops
-                  + t_mlp * (1.0 - block_share) * step_flops / mlp_flops)
-    t_total += t_mlp
-    sample_flops += mlp_flops
-    return {"value": 1.0 / est_step_s, "unit": "forecast-steps/s", "cores": cores, "kind": "port",
-            "sample": f"one Swin3D block per U-Net stage at full width"
-                      f"{'' if lat_fraction == 1 else f', first 1/{lat_fraction} of the latitude rows'} "
-                      f"+ a slice of the Perceiver-decoder MLP ({'; '.join(parts)}; warm pass of two), fp32, "
-                      f"{sample_flops / 1e12:.2f} of {step_flops / 1e12:.1f} TFLOP; step time extrapolated by FLOPs, "
-                      f"blocks and Perceiver GEMMs separately, = {est_step_s:.1f} s",
-            "sample_seconds": t_total}
+        with torch.inference_mode():
+            for sd, x, r, heads in items:
+                O.swin_block(sd, "blk", x, c, r, heads, True, cfg, 0)
+        return time.perf_counter() - t0
+
+    step()
+    times = [step() for _ in range(max(1, n_timed))]
+    med = statistics.median(times)
+    scale = ALGO_TFLOP[workload] * 1e12 / flops
+    return {"value": len(times) / (sum(times) * scale), "unit": "forecast-steps/s", "cores": threads, "kind": "port",
+            "sample_seconds_median": med, "samples": len(times), "sample_scale": scale,
+            "sample": f"oracle PORT (oracle/_ref missing): one shifted Swin block per stage on 1/{SAMPLE_LAT_DIV} of the "
+                      f"latitude rows, fp32, {threads} threads; scaled to a step by algorithmic FLOPs x{scale:.1f}",
+            "_times": times}
+
+
+def cpu_measure(workload: str, n_warm: int, n_timed: int) -> dict:
+    from oracle import ref
+
+    if ref.available():
+        return reference_cpu_measure(workload, n_warm, n_timed)
+    return port_cpu_measure(workload, n_timed)
+
+
+def gpu_reference_measure(workload: str, dev_batch, device) -> dict:
+    """The unmodified reference on the SAME GPU (`model.cuda()`), fp32 (its default) and `autocast=True` (bf16 backbone,
+    the reference's own reduced-precision recipe): the denominator of north_star's ">= 10x the reference single-GPU
+    PyTorch forward".  Batch resident on the device, CUDA events, 1 warm-up + 3 timed forwards, median."""
+    from oracle import ref
+
+    out = {"tf32_matmul_allowed": bool(torch.backends.cuda.matmul.allow_tf32),
+           "sdpa": {"flash": torch.backends.cuda.flash_sdp_enabled(), "mem_efficient": torch.backends.cuda.mem_efficient_sdp_enabled(),
+                    "math": torch.backends.cuda.math_sdp_enabled(),
+                    "note": "the float window mask makes the flash backend ineligible in shifted blocks (SURVEY K2)"},
+           "torch": torch.__version__}
+    rb = ref.to_ref_batch(dev_batch)
+    for tag, autocast in (("fp32", False), ("autocast_bf16", True)):
+        try:
+            model = build_reference(workload, device, autocast=autocast)
+            with torch.inference_mode():
+                model.forward(rb)
+                torch.cuda.synchronize()
+                ts = []
+                for _ in range(3):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    model.forward(rb)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+            out[tag] = {"ms_per_step": statistics.median(ts), "value": 1000.0 / statistics.median(ts),
+                        "unit": "forecast-steps/s", "ms_all": ts,
+                        "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}
+            del model
+        except Exception as e:  # e.g. out of memory on a smaller part: report, do not fail the bench
+            out[tag] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
+    return out
+
+
+def _our_config(workload: str):
+    import aurora_b200 as ab
+
+    return getattr(ab, WORKLOADS[workload][0])(_init="empty").config
 
 
 def gemm_traffic(workload: str, launches: int, algo_bytes: float) -> dict:
@@ -316,31 +392,41 @@ def gemm_traffic(workload: str, launches: int, algo_bytes: float) -> dict:
 
 
 # ------------------------------------------------------------------------------------------------
+def resolve_parallelism(gpus: int, mode: str) -> str:
+    if gpus <= 1:
+        return "single GPU"
+    return "replicas" if mode == "replicas" else "latshard"
+
+
+def workload_config(workload: str, gpus: int = 1, mode: str = "auto") -> dict:
+    """`config`: identical in both arms for the same command line (the driver compares it between the arms)."""
+    cls, h, w, levels = WORKLOADS[workload]
+    par = resolve_parallelism(gpus, mode)
+    return {"workload": workload, "model_class": cls, "grid": f"{h}x{w}", "levels": len(levels), "batch": 1,
+            "history": 2, "algorithmic_tflop_per_step": ALGO_TFLOP[workload],
+            "parallelism": {"single GPU": "single GPU", "replicas": f"replicas x{gpus} (one forecast per GPU)",
+                            "latshard": f"one forecast latitude-sharded over {gpus} GPUs"}[par],
+            "l2": "inputs and activations are GBs per step (>> 126 MB L2): no explicit flush between iterations"}
+
+
 def run_reference_arm(args) -> None:
+    """`--impl reference`: the reference's own CPU implementation on the host cores (rank 0 only).  W + K steps, each
+    the SAME bounded sample (independent of K), plus one complete forward that calibrates sample -> step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    vals, ms = [], []
-    base = None
-    # one full-size sample costs ~25 s on 128 cores; keep the whole run within a few minutes by shrinking the
-    # latitude extent of the per-step sample when many steps are asked for
-    n_samples = args.warmup + args.steps
-    lat_fraction = 1 if n_samples <= 4 else 2 if n_samples <= 8 else 4
-    for i in range(n_samples):
-        base = cpu_baseline_sample(args.workload, cores, lat_fraction)
-        if i >= args.warmup:
-            vals.append(base["value"])
-    v = statistics.mean(vals)
-    cls, h, w, levels = WORKLOADS[args.workload]
+    m = cpu_measure(args.workload, args.warmup, args.steps)
+    times = m.pop("_times")
+    v = m["value"]
     line = {
         "impl": "reference", "metric": "forecast-steps/sec", "value": v, "unit": "forecast-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        # wall time of one timed (bounded-sample) step; a whole forecast step is `sample_scale` times that
+        "ms_per_step": 1000.0 * sum(times) / len(times), "ms_per_whole_step": 1000.0 / v,
+        "sample_scale": m.get("sample_scale"),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "model": cls, "grid": f"{h}x{w}", "levels": len(levels),
-                   "note": "CPU oracle port of the reference algorithm; each step is a bounded sample "
-                           "extrapolated by algorithmic FLOPs"},
-        "cpu_baseline": {**base, "value": v},
+        "config": workload_config(args.workload, args.gpus, args.parallelism),
+        "cpu_baseline": m,
         "e2e": {"value": v, "unit": "forecast-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -354,9 +440,17 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--parallelism", default="replicas", choices=["replicas", "latshard"],
-                    help="N > 1: independent forecasts per GPU (default) or ONE forecast sharded by latitude")
-    ap.add_argument("--cuda-graph", action="store_true", help="model.use_cuda_graph = True (step replayed from a graph)")
+    ap.add_argument("--parallelism", default="auto", choices=["auto", "replicas", "latshard"],
+                    help="N > 1: ONE forecast sharded by latitude over the N GPUs with a halo exchange per Swin block "
+                         "(latshard; `auto` picks it whenever N > 1) or independent forecasts per GPU (replicas)")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+                    help="latshard halo exchange: kernels writing straight into the neighbours' memory over NVLink inside "
+                         "the step's CUDA graph (peer), or NCCL send/recv between graph segments (nccl)")
+    ap.add_argument("--cuda-graph", dest="cuda_graph", action="store_true", default=None,
+                    help="replay the step from a captured CUDA graph (default: on for latshard, off otherwise)")
+    ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false")
+    ap.add_argument("--no-gpu-reference", action="store_true",
+                    help="skip timing the unmodified reference on the same GPU (N = 1 only)")
     ap.add_argument("--rollout", type=int, default=0, metavar="N",
                     help="also time one N-step autoregressive rollout (BASELINE configs[2]: 40) and add a `rollout` object")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -385,7 +479,6 @@ def main() -> None:
     cls, h, w, levels = WORKLOADS[args.workload]
     model = getattr(ab, cls)(_init="empty").to(dev).eval()
     randomise_parameters_(model, seed=rank)
-    model.use_cuda_graph = bool(args.cuda_graph)
     cfg = model.config
     host_batch = make_host_batch(cfg, h, w, levels, pinned=True, seed=rank)
     dev_batch = host_batch.to(dev)
@@ -397,16 +490,22 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    latshard = distributed and args.parallelism == "latshard"
+    latshard = distributed and args.parallelism in ("auto", "latshard")
+    if args.cuda_graph is None:
+        args.cuda_graph = latshard
+    model.use_cuda_graph = bool(args.cuda_graph)
+    plain_forward = model.forward
     if latshard:
-        args.no_e2e = True  # the end-to-end leg is defined for whole forecasts per rank
-        _fwd = model.forward
-        model.forward = lambda b: _fwd(b, sharded=True)  # noqa: E731
+        model.halo_mode = args.halo
+        model.forward = lambda b: plain_forward(b, sharded=True)  # noqa: E731
 
     # ---- warm-up (packs weights, allocates workspace, caches encodings) ----
     for _ in range(args.warmup):
         pred = model.forward(dev_batch)
     d2h_bytes = sum(v.numel() * 4 for d in (pred.surf_vars, pred.atmos_vars) for v in d.values())
+    if latshard:  # every rank uploads only its own latitude band of the (cropped) fields
+        band_rows = next(iter(pred.surf_vars.values())).shape[-2]
+        h2d_bytes = h2d_bytes // h * band_rows
     host_out = {k: torch.empty(v.shape, dtype=torch.float32, pin_memory=True)
                 for d in (pred.surf_vars, pred.atmos_vars) for k, v in d.items()}
 
@@ -464,6 +563,23 @@ def main() -> None:
                         "value": world * 1000.0 * args.rollout / r_ms, "unit": "forecast-steps/s",
                         "note": "aurora_b200.rollout from a pinned host batch; history slide and predictions on the device"}
 
+    # ---- N > 1, sharded: the same box running N independent forecasts instead (secondary number) ----
+    replicas_info = None
+    if latshard:
+        model.use_cuda_graph = False
+        k = max(2, args.steps // 2)
+        plain_forward(dev_batch)
+        barrier()
+        e0.record()
+        for _ in range(k):
+            plain_forward(dev_batch)
+        e1.record()
+        barrier()
+        r_ms = abd.max_over_ranks([e0.elapsed_time(e1) / k], device=dev)[0]
+        replicas_info = {"value": world * 1000.0 / r_ms, "unit": "forecast-steps/s", "ms_per_step": r_ms, "steps": k,
+                         "note": f"{world} independent forecasts, one per GPU, no data-path collective (weak scaling)"}
+        model.use_cuda_graph = bool(args.cuda_graph)
+
     # ---- per-kernel timing for the roofline (one instrumented step; CUDA events around each launch) ----
     cabi.PROFILE = {}
     model.use_cuda_graph = False
@@ -509,42 +625,59 @@ def main() -> None:
         },
     }
 
-    # ---- max over ranks ----
+    # ---- max over ranks (times); bytes moved are summed over ranks for a sharded forecast ----
     if distributed:
         mx = abd.max_over_ranks([ms, e2e_ms or 0.0], device=dev)
         ms, e2e_ms = mx[0], (mx[1] if e2e_ms is not None else None)
+        if latshard:
+            t = torch.tensor([float(h2d_bytes), float(d2h_bytes)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t)
+            h2d_bytes, d2h_bytes = int(t[0].item()), int(t[1].item())
 
     if rank == 0:
-        cpu = None
+        cpu = gpu_ref = None
+        if world == 1 and not args.no_gpu_reference:
+            from oracle import ref as _ref
+
+            if _ref.available():
+                gpu_ref = gpu_reference_measure(args.workload, dev_batch, dev)
+                if "fp32" in gpu_ref and "ms_per_step" in gpu_ref["fp32"]:
+                    for tag in ("fp32", "autocast_bf16"):
+                        if "ms_per_step" in gpu_ref.get(tag, {}):
+                            gpu_ref[tag]["ours_over_reference"] = gpu_ref[tag]["ms_per_step"] / ms
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_baseline_sample(args.workload, os.cpu_count() or 1)
+            cpu = cpu_measure(args.workload, 1, 3)
+            cpu.pop("_times", None)
         algo_tflop = ALGO_TFLOP[args.workload]
         line = {
             "metric": "forecast-steps/sec", "value": (1 if latshard else world) * 1000.0 / ms, "unit": "forecast-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong" if latshard else "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {
-                "workload": args.workload, "model_class": cls, "grid": f"{h}x{w}", "levels": len(levels),
-                "batch_per_gpu": 1, "history": 2, "parameters_m": round(sum(p.numel() for p in model.parameters()) / 1e6, 1),
+            "config": workload_config(args.workload, world, args.parallelism),
+            "details": {
+                "parameters_m": round(sum(p.numel() for p in model.parameters()) / 1e6, 1),
                 "precision": "bf16 operands in the Swin backbone, fp16 operands in encoder/decoder, fp32 accumulate/"
                              "residual/LN/softmax",
-                "parallelism": (f"one forecast latitude-sharded over {world} GPUs, NCCL halo exchange per block"
+                "parallelism": ((f"one forecast latitude-sharded over {world} GPUs, halo exchange per Swin block "
+                                 f"({'peer-memory kernels over NVLink inside the CUDA graph' if args.halo == 'peer' else 'NCCL send/recv'})")
                                 if latshard else f"replicas x{world}") if world > 1 else "single GPU",
-                "l2_note": "inputs and activations are GBs per step (>> 126 MB L2); no explicit flush needed",
-                "algorithmic_tflop_per_step": algo_tflop,
                 "cuda_graph": bool(args.cuda_graph),
             },
             "model_tflops_achieved": algo_tflop / (ms / 1e3),
             "clocks": clocks,
             "gpu_launches": launches,
             "e2e": None if e2e_ms is None else {
-                "value": world * 1000.0 / e2e_ms, "unit": "forecast-steps/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "value": (1 if latshard else world) * 1000.0 / e2e_ms, "unit": "forecast-steps/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": h2d_bytes * (1 if latshard else world),
+                "d2h_bytes_per_step": d2h_bytes * (1 if latshard else world),
             },
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "gpu_reference": gpu_ref,
         }
+        if replicas_info is not None:
+            line["replicas"] = replicas_info
         if rollout_info is not None:
             if distributed:
                 rollout_info["note"] += " (rank 0's time)"

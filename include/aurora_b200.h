@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define AB_ABI_VERSION 1
+#define AB_ABI_VERSION 2
 
 typedef enum AbStatus {
   AB_OK = 0,

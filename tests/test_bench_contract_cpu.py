@@ -1,5 +1,5 @@
-"""bench.py contract checks that need no GPU: the reference arm (CPU oracle port) prints ONE JSON line with the keys
-the driver reads, on rank 0 only, and the ncu summariser parses a metrics CSV."""
+"""bench.py contract checks that need no GPU: the reference arm (the unmodified reference from oracle/_ref on the host
+cores) prints ONE JSON line with the keys the driver reads, on rank 0 only, and the ncu summariser parses a metrics CSV."""
 
 import gzip
 import json
@@ -24,10 +24,14 @@ def test_reference_arm_prints_one_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "forecast-steps/sec" and d["unit"] == "forecast-steps/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1
-    assert d["value"] > 0 and abs(d["ms_per_step"] - 1000.0 / d["value"]) < 1e-6 * d["ms_per_step"]
-    assert d["config"]["workload"] == "aurora-small-17x32x4L"
+    # `ms_per_step` is the wall time of one timed (bounded-sample) step — K of them fit in the run — and a whole forecast
+    # step is `sample_scale` of them, the factor measured against ONE complete reference forward in the same run
+    assert d["value"] > 0 and abs(d["ms_per_whole_step"] - 1000.0 / d["value"]) < 1e-6 * d["ms_per_whole_step"]
+    assert abs(d["ms_per_step"] * d["sample_scale"] / d["ms_per_whole_step"] - 1.0) < 1e-6
+    assert d["config"]["workload"] == "aurora-small-17x32x4L" and d["config"]["parallelism"] == "single GPU"
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert cb["complete_forward_seconds"] > 0 and cb["samples"] == 2
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
 
