@@ -216,8 +216,9 @@ class AuroraEngine:
         key = (prefix, lora_idx)
         w = self._lora.get(key)
         if w is None:
-            if self.cfg.lora_mode == "all" and len(self._lora) > 4 * 64:
-                self._lora.clear()  # one merged copy per step would not fit; keep a sliding set
+            # Every merged copy stays resident (`lora_mode="all"`: one per roll-out step, 40 x 0.8 GB for the 1.3 B
+            # model — sized for 180 GB of HBM): nothing is re-merged on the per-step path and no captured CUDA graph
+            # can be left pointing at a freed weight.
             wq, wp = self.p[f"{prefix}.attn.qkv.weight"].detach(), self.p[f"{prefix}.attn.proj.weight"].detach()
             if lora_idx is not None:
                 a = self.p[f"{prefix}.attn.lora_qkv.loras.{lora_idx}.lora_A"].detach()
@@ -982,7 +983,9 @@ class AuroraEngine:
                 atmos_vars={k: v.clone() for k, v in batch.atmos_vars.items()},
                 metadata=batch.metadata,
             )
-            sprep = dict(prep, batch=static, abs_emb=prep["abs_emb"].clone())
+            # location-dependent inputs that are NOT Batch fields get static copies too: the captured launches bake
+            # their device pointers, and a later batch may bring another grid (lat / lon) or time stamp
+            sprep = dict(prep, batch=static, abs_emb=prep["abs_emb"].clone(), posscale=prep["posscale"].clone())
             self._run(sprep)
             torch.cuda.synchronize()
             # Segmented capture on a side stream: `_exchange` splits the step at every halo exchange.  All
@@ -1000,7 +1003,7 @@ class AuroraEngine:
                     self._capture = None
                 items = cap["items"] + [cap["graph"]]
             torch.cuda.current_stream().wait_stream(side)
-            entry = {"items": items, "prep": sprep, "outs": outs}
+            entry = {"items": items, "prep": sprep, "outs": outs, "posscale_src": prep["posscale"]}
             self._graphs[sig] = entry
         sprep = entry["prep"]
         sb = sprep["batch"]
@@ -1010,9 +1013,15 @@ class AuroraEngine:
                 if dst[k].data_ptr() != v.data_ptr():
                     dst[k].copy_(v)
         sprep["abs_emb"].copy_(prep["abs_emb"])
+        if entry["posscale_src"] is not prep["posscale"]:  # another grid with the same shapes (a moved regional domain)
+            sprep["posscale"].copy_(prep["posscale"])
+            entry["posscale_src"] = prep["posscale"]
         for item in entry["items"]:
             if isinstance(item, torch.cuda.CUDAGraph):
                 item.replay()
             else:
                 item()  # halo exchange between two graph segments
-        return self._finish(prep, *entry["outs"])
+        # hand out copies (0.3 GB device-to-device, ~0.1 ms): predictions must not alias the graph's static output
+        # buffers, or `list(rollout(...))` would hold the last step's data in every entry
+        out_surf, out_atmos = ({k: v.clone() for k, v in d.items()} for d in entry["outs"])
+        return self._finish(prep, out_surf, out_atmos)

@@ -92,9 +92,8 @@ class Aurora(nn.Module):
         self._engine = None
         self._engine_sig = None
         self.use_cuda_graph = False
-        """bool: replay each forward step from a captured CUDA graph (one capture per input signature).
-        Predictions then live in static device buffers that the next `forward` overwrites — copy what you keep
-        (`rollout` does, `pred.to("cpu")` does)."""
+        """bool: replay each forward step from a captured CUDA graph (one capture per input signature).  Predictions
+        are copies of the graph's static output buffers, so they stay valid like the reference's."""
 
     # -- parameter tree ---------------------------------------------------------------------------
     def _extra_specs(self):
@@ -147,6 +146,15 @@ class Aurora(nn.Module):
         `sharded=True` (one process per GPU under `torch.distributed`): every rank passes the same batch and
         gets back ITS latitude band of the prediction (see `aurora_b200/sharding.py`; `gather_bands` rebuilds
         full fields)."""
+        if not self.autocast:
+            # The reference's default (`autocast=False`, aurora.py:84) is a pure fp32 forward.  Blackwell has no fp32
+            # tensor-core path and this engine has no 3-pass split mode: it always computes with 16-bit operands and
+            # fp32 accumulation, the reference's `autocast=True` recipe (aurora.py:327-343).  Running that under a
+            # flag that promises fp32 would be a silent precision change, so it is refused.
+            raise NotImplementedError(
+                "aurora_b200 computes with bf16 / fp16 tensor-core operands and fp32 accumulation (the reference's "
+                "`autocast=True` recipe) and has no fp32-exact mode: construct the model with `autocast=True` (or set "
+                "`model.autocast = True`) to run it.")
         batch = self.batch_transform_hook(batch)
         return self._get_engine().forward(batch, sharded=sharded)
 

@@ -477,7 +477,7 @@ def main() -> None:
     distributed = abd.init_process_group("nccl", dev)
 
     cls, h, w, levels = WORKLOADS[args.workload]
-    model = getattr(ab, cls)(_init="empty").to(dev).eval()
+    model = getattr(ab, cls)(_init="empty", autocast=True).to(dev).eval()
     randomise_parameters_(model, seed=rank)
     cfg = model.config
     host_batch = make_host_batch(cfg, h, w, levels, pinned=True, seed=rank)

@@ -212,6 +212,18 @@ def reference_kwargs(cfg: ModelConfig) -> dict:
     return kw
 
 
+# The reference's own acceptance budget for its stored outputs, per variable, as rel-mean-abs error
+# mean|out - ref| / mean|ref| (reference tests/test_model.py:45-61: 1e-4 for 2t / msl / t, 5e-3 for winds and humidity;
+# z, which the reference's stored outputs do not cover, is held to the tight bound like t).  Everything else (air
+# pollution / wave variables, which the reference never pins) takes the loose bound.
+REF_TOL = {"2t": 1e-4, "msl": 1e-4, "t": 1e-4, "z": 1e-4, "10u": 5e-3, "10v": 5e-3, "u": 5e-3, "v": 5e-3, "q": 5e-3}
+REF_TOL_DEFAULT = 5e-3
+
+
+def tol_for(name: str) -> float:
+    return REF_TOL.get(name, REF_TOL_DEFAULT)
+
+
 def rel_mean_abs(out: torch.Tensor, ref: torch.Tensor) -> float:
     """The reference's own acceptance metric: mean|out - ref| / mean|ref| (tests/test_model.py:45-61)."""
     return float((out.double() - ref.double()).abs().mean() / ref.double().abs().mean().clamp_min(1e-30))
@@ -251,4 +263,13 @@ def model_kwargs(cfg: ModelConfig, cls_name: str) -> dict:
     kw = reference_kwargs(cfg)
     if cls_name == "AuroraWave":  # the class derives the modelled channels from the raw variable names itself
         kw["surf_vars"] = WAVE_RAW_SURF
+    return kw
+
+
+def our_kwargs(cfg: ModelConfig, cls_name: str = "Aurora") -> dict:
+    """Constructor arguments for an `aurora_b200` model equivalent to `cfg`: as `model_kwargs`, with `autocast=True`.
+    aurora_b200 computes with 16-bit tensor-core operands — the reference's `autocast=True` recipe — and refuses to run
+    a model that asks for the reference's fp32 default (`aurora_b200/model.py`)."""
+    kw = model_kwargs(cfg, cls_name)
+    kw["autocast"] = True
     return kw

@@ -12,7 +12,7 @@ from tests import fixtures as fx
 
 def _tiny():
     cfg = fx.CONFIGS["tiny"]
-    return cfg, ab.Aurora(**fx.reference_kwargs(cfg), _init_seed=0)
+    return cfg, ab.Aurora(**fx.our_kwargs(cfg), _init_seed=0)
 
 
 def test_cpu_parameters_raise():
@@ -25,6 +25,19 @@ def test_double_parameters_raise_not_implemented():
     cfg, model = _tiny()
     with pytest.raises(NotImplementedError, match="fp32 master parameters"):
         model.double().forward(fx.make_batch(cfg, 17, 32, levels=fx.LEVELS4))
+
+
+def test_fp32_default_is_refused_not_silently_downgraded():
+    """`Aurora()` defaults to `autocast=False` = pure fp32 in the reference (aurora.py:84); the engine only has the
+    `autocast=True` arithmetic, so `forward` refuses until the caller opts in."""
+    cfg = fx.CONFIGS["tiny"]
+    model = ab.Aurora(**fx.reference_kwargs(cfg), _init_seed=0)
+    assert model.autocast is False
+    with pytest.raises(NotImplementedError, match="autocast=True"):
+        model.forward(fx.make_batch(cfg, 17, 32, levels=fx.LEVELS4))
+    model.autocast = True
+    with pytest.raises(RuntimeError, match="CUDA devices only"):  # past the precision gate: now only the device is wrong
+        model.forward(fx.make_batch(cfg, 17, 32, levels=fx.LEVELS4))
 
 
 def test_training_features_raise():

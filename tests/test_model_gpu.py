@@ -4,9 +4,11 @@
 
 Stated tolerance: the path computes with bf16 GEMM operands and fp32 accumulation / residuals /
 statistics (the reference's autocast recipe).  Per variable, rel-mean-abs error
-mean|out-ref| / mean|ref| must stay within the reference's own acceptance budget for its stored
-outputs (tests/test_model.py:45-61): 5e-3 for every variable; the measured values are printed."""
+mean|out-ref| / mean|ref| must stay within the reference's own PER-VARIABLE acceptance budget for its
+stored outputs (reference tests/test_model.py:45-61, `tests/fixtures.py:REF_TOL`): 1e-4 for 2t / msl / t / z,
+5e-3 for winds, humidity and the variables the reference never pins; the measured values are printed."""
 
+import dataclasses
 from pathlib import Path
 
 import numpy as np
@@ -18,7 +20,6 @@ from tests.golden.cases import MODEL_CASES
 
 pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).parent / "golden"
-TOL = 5e-3
 NAN_TOL = 5e-3
 
 CLASS_OF = {"Aurora": "Aurora", "AuroraAirPollution": "AuroraAirPollution", "AuroraSmallPretrained": "AuroraSmallPretrained"}
@@ -28,8 +29,8 @@ def _build(cfg_name, cls_name, seed):
     import aurora_b200 as ab
 
     cfg = fx.CONFIGS[cfg_name]
-    model = getattr(ab, cls_name)(**fx.model_kwargs(cfg, cls_name))
-    assert model.config == cfg
+    model = getattr(ab, cls_name)(**fx.our_kwargs(cfg, cls_name))
+    assert dataclasses.replace(model.config, autocast=False) == cfg   # only `autocast` differs (see fx.our_kwargs)
     extra = fx.air_extra_specs(cfg) if cls_name == "AuroraAirPollution" else ()
     model.load_state_dict(fx.make_state_dict(cfg, seed=seed, extra=extra), strict=True)
     return cfg, model.to("cuda").eval()
@@ -63,7 +64,7 @@ def test_forward_matches_reference_golden(name):
             # on the circle
             err, nan_mismatch = fx.field_error(out, ref, angle=wave and k in fx.WAVE_ANGLES)
             worst = max(worst, err)
-            assert err < TOL and nan_mismatch < NAN_TOL, (name, grp, k, err, nan_mismatch)
+            assert err < fx.tol_for(k) and nan_mismatch < NAN_TOL, (name, grp, k, err, nan_mismatch)
     print(f"[parity] {name}: worst rel-mean-abs {worst:.3e}")
     for k, v in pred.static_vars.items():
         assert torch.equal(v.cpu(), batch.crop(cfg.patch_size).static_vars[k])
@@ -80,7 +81,7 @@ def test_forward_matches_oracle_live_on_new_shape():
         ref = O.forward(cfg, fx.make_state_dict(cfg, seed=11), batch, dtype=torch.float32)
     for grp, d, r in (("surf", pred.surf_vars, ref.surf_vars), ("atmos", pred.atmos_vars, ref.atmos_vars)):
         for k in d:
-            assert fx.rel_mean_abs(d[k].cpu(), r[k]) < TOL, (grp, k)
+            assert fx.rel_mean_abs(d[k].cpu(), r[k]) < fx.tol_for(k), (grp, k)
 
 
 def test_rollout_matches_reference_golden():
@@ -92,9 +93,9 @@ def test_rollout_matches_reference_golden():
     for i, pred in enumerate(ab.rollout(model, batch, steps=3)):
         assert pred.metadata.rollout_step == int(gold[f"step{i}.rollout_step"]) == i + 1
         for k, v in pred.surf_vars.items():
-            assert fx.rel_mean_abs(v.cpu(), torch.from_numpy(gold[f"step{i}.surf.{k}"])) < TOL * (i + 1), (i, k)
+            assert fx.rel_mean_abs(v.cpu(), torch.from_numpy(gold[f"step{i}.surf.{k}"])) < fx.tol_for(k) * (i + 1), (i, k)
         for k, v in pred.atmos_vars.items():
-            assert fx.rel_mean_abs(v.cpu(), torch.from_numpy(gold[f"step{i}.atmos.{k}"])) < TOL * (i + 1), (i, k)
+            assert fx.rel_mean_abs(v.cpu(), torch.from_numpy(gold[f"step{i}.atmos.{k}"])) < fx.tol_for(k) * (i + 1), (i, k)
 
 
 def test_wave_rollout_matches_oracle_live():
@@ -114,14 +115,14 @@ def test_wave_rollout_matches_oracle_live():
         for grp, d, r in (("surf", pred.surf_vars, refs[i].surf_vars), ("atmos", pred.atmos_vars, refs[i].atmos_vars)):
             for k in d:
                 err, nan_mismatch = fx.field_error(d[k].cpu(), r[k], angle=k in fx.WAVE_ANGLES)
-                assert err < TOL * (i + 1) and nan_mismatch < NAN_TOL * (i + 1), (i, grp, k, err, nan_mismatch)
+                assert err < fx.tol_for(k) * (i + 1) and nan_mismatch < NAN_TOL * (i + 1), (i, grp, k, err, nan_mismatch)
 
 
 def test_no_cpu_path():
     import aurora_b200 as ab
 
     cfg = fx.CONFIGS["tiny"]
-    model = ab.Aurora(**fx.reference_kwargs(cfg))
+    model = ab.Aurora(**fx.our_kwargs(cfg))
     with pytest.raises(RuntimeError, match="CUDA"):
         model.forward(fx.make_batch(cfg, 17, 32, levels=fx.LEVELS4))
 
@@ -200,3 +201,52 @@ def test_pinned_host_batches_take_the_overlapped_upload_and_give_the_same_bits(c
             assert torch.equal(p.atmos_vars[k], wa[k]), k
         for k in wst:
             assert torch.equal(p.static_vars[k], wst[k]), k
+
+
+def test_cuda_graph_replay_follows_a_moved_grid():
+    """Same shapes, other lat / lon (a moved regional domain): the position / scale embeddings are inputs of the
+    captured graph like the Batch fields, so the replay must match the eager step on the new grid."""
+    import dataclasses
+
+    from aurora_b200 import Metadata
+
+    cfg, model = _build("tiny_lora", "Aurora", 13)
+    b1 = fx.make_batch(cfg, 33, 64, levels=fx.LEVELS4, b=1, seed=13)
+    md = b1.metadata
+    moved = dataclasses.replace(b1, metadata=Metadata(lat=md.lat * 0.5 + 10.0, lon=(md.lon * 0.5 + 40.0) % 360.0,
+                                                     time=md.time, atmos_levels=md.atmos_levels,
+                                                     rollout_step=md.rollout_step))
+    e1 = {k: v.clone() for k, v in model.forward(b1).atmos_vars.items()}
+    e2 = {k: v.clone() for k, v in model.forward(moved).atmos_vars.items()}
+    assert any(not torch.equal(e1[k], e2[k]) for k in e1)  # the grid matters
+    model.use_cuda_graph = True
+    g1 = model.forward(b1).atmos_vars        # capture
+    g2 = model.forward(moved).atmos_vars     # replay on the moved grid
+    g1b = model.forward(b1).atmos_vars       # and back
+    for k in e1:
+        assert torch.equal(e1[k], g1[k]) and torch.equal(e2[k], g2[k]) and torch.equal(e1[k], g1b[k]), k
+
+
+@pytest.mark.parametrize("lora_mode", ["single", "all"])
+def test_graph_rollout_yields_independent_predictions(lora_mode):
+    """`list(rollout(...))` under `use_cuda_graph`: every entry keeps its own step's data (predictions are copies of the
+    graph's static buffers), two consecutive roll-outs of 8 steps agree with the eager roll-out bit for bit — in
+    `lora_mode="all"` that runs 8 different merged weight sets through graphs captured during the first roll-out."""
+    import dataclasses
+
+    import aurora_b200 as ab
+
+    cfg = dataclasses.replace(fx.CONFIGS["tiny_lora"], lora_mode=lora_mode)
+    model = ab.Aurora(**fx.our_kwargs(cfg))
+    model.load_state_dict(fx.make_state_dict(cfg, seed=19), strict=True)
+    model = model.to("cuda").eval()
+    batch = fx.make_batch(cfg, 33, 64, levels=fx.LEVELS4, b=1, seed=19)
+    eager = [{k: v.clone() for k, v in p.atmos_vars.items()} for p in ab.rollout(model, batch, steps=8)]
+    assert not torch.equal(eager[3]["t"], eager[7]["t"])
+    model.use_cuda_graph = True
+    for _ in range(2):
+        preds = list(ab.rollout(model, batch, steps=8))
+        assert [p.metadata.rollout_step for p in preds] == list(range(1, 9))
+        for i, p in enumerate(preds):
+            for k, v in p.atmos_vars.items():
+                assert torch.equal(v, eager[i][k]), (i, k)

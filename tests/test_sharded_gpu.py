@@ -29,7 +29,7 @@ def _worker(rank, world, port, q):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     cfg = fx.CONFIGS["tiny_lora"]
-    model = ab.Aurora(**fx.reference_kwargs(cfg))
+    model = ab.Aurora(**fx.our_kwargs(cfg))
     model.load_state_dict(fx.make_state_dict(cfg, seed=31))
     model = model.to(f"cuda:{rank}").eval()
     # patch_res (4, 48, 64): full 144-token windows at all three stages, zero padding in W at stage 3

@@ -4,6 +4,7 @@ itself pinned to the reference (tests/test_oracle_golden.py), and against the go
 
 from pathlib import Path
 
+import dataclasses
 import numpy as np
 import torch
 
@@ -18,8 +19,8 @@ GOLD = Path(__file__).parent / "golden"
 
 def test_wave_model_declares_reference_channels():
     cfg = fx.CONFIGS["tiny_wave"]
-    model = ab.AuroraWave(**fx.model_kwargs(cfg, "AuroraWave"))
-    assert model.config == cfg
+    model = ab.AuroraWave(**fx.our_kwargs(cfg, "AuroraWave"))
+    assert dataclasses.replace(model.config, autocast=False) == cfg
     assert model.config.surf_vars == fx.wave_supplemented()
     default = ab.AuroraWave(_init="empty").config  # 1.3 B preset, parameters left uninitialised
     assert default.surf_vars == fx.wave_supplemented() and default.static_vars == fx.WAVE_STATIC
@@ -56,7 +57,7 @@ def test_output_order_matches_reference_golden():
 
 def test_batch_transform_hook_matches_oracle():
     cfg = fx.CONFIGS["tiny_wave"]
-    model = ab.AuroraWave(**fx.model_kwargs(cfg, "AuroraWave"))
+    model = ab.AuroraWave(**fx.our_kwargs(cfg, "AuroraWave"))
     for step, with_dwi in ((0, True), (1, False), (0, False)):
         batch = fx.make_wave_batch(cfg, 33, 64, seed=8, rollout_step=step, with_dwi=with_dwi)
         ours = model.batch_transform_hook(batch)

@@ -14,7 +14,7 @@ from tests.golden.cases import MODEL_CASES  # noqa: E402
 out = {}
 for name, (cfg_name, cls_name, h, w, levels, bsz, step, seed) in MODEL_CASES.items():
     cfg = fx.CONFIGS[cfg_name]
-    model = getattr(ab, cls_name)(**fx.reference_kwargs(cfg))
+    model = getattr(ab, cls_name)(**fx.our_kwargs(cfg, cls_name))
     extra = fx.air_extra_specs(cfg) if cls_name == "AuroraAirPollution" else ()
     model.load_state_dict(fx.make_state_dict(cfg, seed=seed, extra=extra))
     model = model.to("cuda")
