@@ -17,7 +17,8 @@ from aurora_b200 import _build
 __all__ = [
     "lib", "AbError", "check", "ptr", "stream_ptr", "launch_count", "gemm", "window_attention", "window_geometry",
     "window_index_map", "ln_mod_residual", "patch_merge_ln", "patch_split_ln", "perceiver_attention",
-    "linear_small", "patchify", "unpatchify", "AbFieldIn", "AbFieldOut",
+    "linear_small", "patchify", "unpatchify", "AbFieldIn", "AbFieldOut", "ipc_export", "ipc_open", "ipc_close",
+    "halo_push", "halo_wait",
 ]
 
 ABI_VERSION = 2  # == AB_ABI_VERSION in include/aurora_b200.h
@@ -102,7 +103,14 @@ EXPORTS = [
     "ab_linear_small_f32",
     "ab_patchify",
     "ab_unpatchify",
+    "ab_ipc_export",
+    "ab_ipc_open",
+    "ab_ipc_close",
+    "ab_halo_push",
+    "ab_halo_wait",
 ]
+AB_IPC_HANDLE_BYTES = 64
+AB_HALO_CTRL_BYTES = 256
 AB_MAX_FIELDS = 64
 AB_IN_PLAIN, AB_IN_CLAMP_MIN0, AB_IN_CLAMP_LOG_COMBINE = 0, 1, 2
 AB_IN_NAN_TO_ZERO, AB_IN_DENSITY, AB_IN_SIN_DEG, AB_IN_COS_DEG = 3, 4, 5, 6
@@ -449,3 +457,59 @@ def unpatchify(fields: list, y: torch.Tensor, h: int, w: int, p: int) -> None:
     assert y.dtype == torch.float32 and y.dim() == 2 and y.shape[0] == (h // p) * (w // p)
     arr = (AbFieldOut * len(fields))(*fields)
     check(lib().ab_unpatchify(arr, len(fields), C.c_void_p(ptr(y)), _ld(y), h, w, p, _s()), "ab_unpatchify")
+
+
+# ---- peer-memory halo exchange (csrc/halo.cu) ------------------------------------------------------------------
+class AbHaloPush(C.Structure):
+    _fields_ = [
+        ("local", C.c_void_p),
+        ("above_slot", C.c_void_p),
+        ("below_slot", C.c_void_p),
+        ("above_flag", C.c_void_p),
+        ("below_flag", C.c_void_p),
+        ("ctrl", C.c_void_p),
+        ("c", C.c_int32),
+        ("rows", C.c_int32),
+        ("halo", C.c_int32),
+        ("reserved_", C.c_int32),
+        ("row_bytes", C.c_int64),
+    ]
+
+
+def ipc_export(t: torch.Tensor) -> tuple[bytes, int]:
+    """(IPC handle bytes, offset of `t` inside its allocation) for a CUDA tensor of THIS process."""
+    h = (C.c_uint8 * AB_IPC_HANDLE_BYTES)()
+    off = C.c_uint64()
+    check(lib().ab_ipc_export(C.c_void_p(ptr(t)), h, C.byref(off)), "ab_ipc_export")
+    return bytes(h), int(off.value)
+
+
+def ipc_open(handle: bytes) -> int:
+    """Map another process's allocation; returns its base address in this process."""
+    assert len(handle) == AB_IPC_HANDLE_BYTES
+    h = (C.c_uint8 * AB_IPC_HANDLE_BYTES).from_buffer_copy(handle)
+    base = C.c_void_p()
+    check(lib().ab_ipc_open(h, C.byref(base)), "ab_ipc_open")
+    return int(base.value)
+
+
+def ipc_close(base: int) -> None:
+    check(lib().ab_ipc_close(C.c_void_p(base)), "ab_ipc_close")
+
+
+def halo_push(local: torch.Tensor, *, above_slot: int, below_slot: int, above_flag: int, below_flag: int, ctrl: int,
+              halo: int) -> None:
+    """`local` [C, rows, X] contiguous (any 2-byte dtype); the slot / flag arguments are raw (peer) addresses."""
+    assert local.dim() == 3 and local.is_contiguous()
+    a = AbHaloPush()
+    a.local = ptr(local)
+    a.above_slot, a.below_slot, a.above_flag, a.below_flag, a.ctrl = above_slot, below_slot, above_flag, below_flag, ctrl
+    a.c, a.rows, a.halo = local.shape[0], local.shape[1], halo
+    a.row_bytes = local.shape[2] * local.element_size()
+    with _Timed("halo_push", nbytes=2.0 * a.c * halo * a.row_bytes):
+        check(lib().ab_halo_push(C.byref(a), _s()), "ab_halo_push")
+
+
+def halo_wait(ctrl: int) -> None:
+    with _Timed("halo_wait"):
+        check(lib().ab_halo_wait(C.c_void_p(ctrl), _s()), "ab_halo_wait")

@@ -347,38 +347,36 @@ __global__ void __launch_bounds__(kAttnThreads, 2) window_attention_kernel(const
 // tcgen05 / TMEM attention for FULL windows (2 x 6 x 12 = 144 tokens, head_dim 64): the production case.
 //
 // Persistent CTA per SM, warp-specialised, one (window, head) item per pipeline slot:
-//   warps 0-1 : loaders.  Warp w gathers the q/k/v rows of items n = w (mod 2) into smem stage w with cp.async
-//               (128-byte rows, hardware 128B-swizzle pattern: chunk ^= row & 7), computes the index map and
-//               group ids for that item (window_index.cuh), then makes the data visible to the async proxy.
+//   warps 0-1 : loaders.  Warp w handles items n = w (mod 2): index map + group ids by closed form
+//               (window_index.cuh), then a TMA ROW-BOX GATHER of the window's q / k / v rows into a FOUR-stage
+//               128B-swizzled ring (bias rows for zero-padded tokens are filled by the warp itself).
 //   warp 2    : MMA issuer (one lane).  S = Q K^T as two M=128 x N=144 x K=64 tcgen05.mma tiles (rows 0-127 and
-//               32-159 of the Q tile; rows >= 144 are don't-care), accumulators in TMEM; later
-//               O = P V as two M=128 x N=64 x K=144 tiles with V as an MN-major B operand straight from the
-//               gathered [key][d] rows.  S(n+1) is issued before P V(n), so the tensor pipe works under the softmax.
+//               32-159 of the Q tile; rows >= 144 are don't-care), accumulators in TMEM; O = P V as two
+//               M=128 x N=64 x K=144 tiles with **P AS THE TMEM A OPERAND** (`tcgen05.mma [d], [a_tmem], b_desc`) and
+//               V as an MN-major B operand straight from the gathered [key][d] rows.  S0(n+1) is issued as soon as
+//               the tile-0 warps hold S0(n) in registers; S1(n+1) after P V(n), because P of tile 1 lives in the
+//               first 72 columns of S1 and the tensor pipe executes in issue order.
 //   warps 3-7 : softmax + epilogue, ONE THREAD PER QUERY ROW (TMEM lane = row): tcgen05.ld the 144 logits, add
 //               the 0 / -100 shifted-window mask from one byte of group id per key, max / exp2 / sum without any
-//               shuffle, write P (bf16) into K-major swizzled smem, and — one item later — read O, scale by
-//               1 / sum and store the 128-byte output row at the source token (reverse + crop + un-roll).
-// TMEM columns: S tile 0 [0,144), O tile 0 [160,224), S tile 1 [256,400), O tile 1 [416,480).
+//               shuffle, write P (bf16 pairs) back to TMEM with tcgen05.st — no shared-memory round trip, no
+//               generic->async proxy fence — and, one item later, read O, scale by 1 / sum and store the 128-byte
+//               output row at the source token (reverse + crop + un-roll).
+// History (profiles/r01p_ncu_final_captures.md, r02 probe): the round-1 kernel wrote P to swizzled shared memory
+// (26 % of the softmax warps' samples in STS + fence) with a three-stage ring; P in TMEM + the 4th stage in the freed
+// 54 KB measured 7-12 % faster on the three stage grids, bit-identical output.
 // ================================================================================================
 namespace tc {
 
 constexpr int kTok = 144;
 constexpr int kTileBytes = kTok * kRowBytes;       // 18 KB per q / k / v tile
 constexpr int kStageBytes = 3 * kTileBytes;        // 54 KB
-constexpr int kP0BlockBytes = 128 * kRowBytes;     // 16 KB: 128 rows x 64 keys
-constexpr int kStages = 3;                         // q/k/v ring: a stage is only released by P V, loads must run ahead
-constexpr int kP1BlockBytes = 16 * kRowBytes;      // tile 1: only rows 128..143 (TMEM lanes 96..111) are real -> 2 KB
-constexpr int kOffP0 = kStages * kStageBytes;      // 162 KB
-constexpr int kOffP1 = kOffP0 + 3 * kP0BlockBytes; // 210 KB: three 2 KB blocks holding tile-1 rows 96..111
-constexpr int kOffMeta = kOffP1 + 3 * kP1BlockBytes;  // 216 KB
-constexpr int kMetaBytes = 4352;
-// The tile-1 A operand of P V starts 96 rows BEFORE its live rows (inside the P0 area): the M=128 MMA reads 128
-// rows, rows 0..95 / 112..127 are don't-care (their accumulator rows are never read) but must be mapped memory.
-constexpr int kP1Rewind = 96 * kRowBytes;
+constexpr int kStages = 4;                         // q/k/v ring: a stage is only released by P V, loads must run ahead
+constexpr int kOffMeta = kStages * kStageBytes;    // 216 KB
+constexpr int kMetaBytes = 6144;
 constexpr int kSmemBytes = kOffMeta + kMetaBytes + 1024;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory");
 constexpr int kThreads = 8 * 32;  // two warps per scheduler: every thread may use up to 255 registers
 constexpr int kTile1Row0 = 32;    // tile 1 covers Q rows 32..159, so rows 128..143 sit in TMEM lanes 96..111 (warp 3)
-constexpr uint32_t kColS0 = 0, kColO0 = 160, kColS1 = 256, kColO1 = 416;
 
 // win_source_token() for the fixed (2, 6, 12) window with the window already decoded to (k0, k1, k2):
 // compile-time divisors only (the generic routine's runtime divisions made the single loader warp the
@@ -472,16 +470,52 @@ __device__ __forceinline__ void tc_translate(const AttnArgs& a, int src, int* lo
   *load_row = kHaloFlag | (((g.res[0] + c) * a.halo + db) * g.res[2] + w);  // host guarantees db < halo
 }
 
+// TMEM columns (all multiples of 16): S0 [0,144)  P0 [144,216)  O0 [224,288)  S1 [288,432) with P1 = [288,360)  O1 [432,496)
+constexpr uint32_t kColS0 = 0, kColP0 = 144, kColO0 = 224, kColS1 = 288, kColP1 = kColS1, kColO1 = 432;
+
 struct Meta {
-  int lsrc[kStages][kTok];  // row to load from (kHaloFlag: halo buffer), -1 = zero padding
+  int lsrc[kStages][kTok];
   int src[kStages][kTok];
   alignas(16) uint8_t grp[kStages][kTok + 16];
   int masked[kStages];
-  int pad_;
-  uint64_t full[kStages], empty[kStages], s_full, s_free, p_full, o_full, o_free;
+  int head[kStages];
+  int batch[kStages];
+  uint64_t full[kStages], empty[kStages], s0_full, s1_full, s0_free, p_full, o_full, o_free;
   uint32_t tmem_slot;
 };
 static_assert(sizeof(Meta) <= kMetaBytes, "meta area");
+
+// D[tmem] (+)= A[tmem] * B[smem]^T : A = 128 lanes x 8 columns of packed 16-bit pairs (K = 16) per instruction.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// registers -> TMEM: this warp's 32 lanes x 32 / 8 consecutive 32-bit columns (thread t writes lane t).
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __global__ void __launch_bounds__(kThreads, 1)
 window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_halo,
@@ -506,8 +540,9 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
       mbar_init(&meta->full[i], 1);
       mbar_init(&meta->empty[i], 1);
     }
-    mbar_init(&meta->s_full, 1);
-    mbar_init(&meta->s_free, 5);
+    mbar_init(&meta->s0_full, 1);
+    mbar_init(&meta->s1_full, 1);
+    mbar_init(&meta->s0_free, 4);  // only the four tile-0 warps release S0 (S1 is re-issued after P V, in pipe order)
     mbar_init(&meta->p_full, 5);
     mbar_init(&meta->o_full, 1);
     mbar_init(&meta->o_free, 5);
@@ -543,7 +578,11 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
         meta->grp[st][t] = static_cast<uint8_t>(grp);
       }
       const int masked = (__any_sync(0xffffffffu, differs) && g.shifted) ? 1 : 0;
-      if (lane == 0) meta->masked[st] = masked;
+      if (lane == 0) {
+        meta->masked[st] = masked;
+        meta->head[st] = it.head;   // the epilogue takes (batch, head) from here instead of re-decoding the item
+        meta->batch[st] = it.b;
+      }
       __syncwarp();
       const long long row_base = static_cast<long long>(it.b) * a.tokens_per_batch;
       if (a.box_rows > 0) {
@@ -611,43 +650,51 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
     if (lane == 0 && cnt > 0) {
       // ===== MMA issuer =====
       constexpr uint32_t idesc_s = umma_idesc_f16kind_f32(128, kTok, false);
-      constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(128, kHeadDim);
-      auto issue_s = [&](int n) {
+      constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(128, kHeadDim);  // A (now in TMEM) K-major, B = V MN-major
+      // S tile 0 and S tile 1 are issued (and signalled) separately.  S0(n+1) goes out as soon as the tile-0
+      // warps hold S0(n) in registers (tensor work under the softmax, as before); S1(n+1) is issued AFTER P V(n),
+      // because P of tile 1 lives in the first 72 columns of S1 and tcgen05.mma executes in issue order.
+      auto issue_s0 = [&](int n) {
         const uint32_t qa = smem_u32(smem + (n % kStages) * kStageBytes);
         const uint32_t ka = qa + kTileBytes;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t db = umma_desc_k_sw128(ka + k * 32);
-          umma_bf16_ss(tmem_base + kColS0, umma_desc_k_sw128(qa + k * 32), db, idesc_s, k != 0);
-          umma_bf16_ss(tmem_base + kColS1, umma_desc_k_sw128(qa + kTile1Row0 * kRowBytes + k * 32), db, idesc_s, k != 0);
-        }
-        umma_commit(&meta->s_full);
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tmem_base + kColS0, umma_desc_k_sw128(qa + k * 32), umma_desc_k_sw128(ka + k * 32), idesc_s, k != 0);
+        umma_commit(&meta->s0_full);
+      };
+      auto issue_s1 = [&](int n) {
+        const uint32_t qa = smem_u32(smem + (n % kStages) * kStageBytes);
+        const uint32_t ka = qa + kTileBytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tmem_base + kColS1, umma_desc_k_sw128(qa + kTile1Row0 * kRowBytes + k * 32),
+                       umma_desc_k_sw128(ka + k * 32), idesc_s, k != 0);
+        umma_commit(&meta->s1_full);
       };
       mbar_wait(&meta->full[0], 0);
       tc_fence_after_sync();
-      issue_s(0);
+      issue_s0(0);
+      issue_s1(0);
       for (int n = 0; n < cnt; ++n) {
         if (n + 1 < cnt) {
           mbar_wait(&meta->full[(n + 1) % kStages], ((n + 1) / kStages) & 1);
-          mbar_wait(&meta->s_free, n & 1);  // the softmax warps have pulled S(n) out of TMEM
+          mbar_wait(&meta->s0_free, n & 1);  // the tile-0 softmax warps have pulled S0(n) out of TMEM
           tc_fence_after_sync();
-          issue_s(n + 1);
+          issue_s0(n + 1);
         }
-        mbar_wait(&meta->p_full, n & 1);
+        mbar_wait(&meta->p_full, n & 1);     // P(n) is in TMEM (tcgen05.st + wait::st + fence on the writer side)
         if (n > 0) mbar_wait(&meta->o_free, (n - 1) & 1);
         tc_fence_after_sync();
         const uint32_t va = smem_u32(smem + (n % kStages) * kStageBytes) + 2 * kTileBytes;
-        const uint32_t p0 = smem_u32(smem + kOffP0), p1 = smem_u32(smem + kOffP1) - kP1Rewind;
 #pragma unroll
-        for (int j = 0; j < kTok / 16; ++j) {  // 9 k-steps of 16 keys
+        for (int j = 0; j < kTok / 16; ++j) {  // 9 k-steps of 16 keys = 8 TMEM columns of packed bf16 pairs each
           const uint64_t dv = umma_desc_k_sw128(va + j * 16 * kRowBytes);
-          umma_bf16_ss(tmem_base + kColO0, umma_desc_k_sw128(p0 + (j >> 2) * kP0BlockBytes + (j & 3) * 32), dv, idesc_o,
-                       j != 0);
-          umma_bf16_ss(tmem_base + kColO1, umma_desc_k_sw128(p1 + (j >> 2) * kP1BlockBytes + (j & 3) * 32), dv, idesc_o,
-                       j != 0);
+          umma_bf16_ts(tmem_base + kColO0, tmem_base + kColP0 + j * 8, dv, idesc_o, j != 0);
+          umma_bf16_ts(tmem_base + kColO1, tmem_base + kColP1 + j * 8, dv, idesc_o, j != 0);
         }
         umma_commit(&meta->o_full);
         umma_commit(&meta->empty[n % kStages]);  // q / k / v of this stage are consumed
+        if (n + 1 < cnt) issue_s1(n + 1);        // overwrites P1(n) only after P V(n) above has read it
       }
     }
   } else {
@@ -659,15 +706,15 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t s_addr = tmem_base + lane_addr + (tile ? kColS1 : kColS0);
     const uint32_t o_addr = tmem_base + lane_addr + (tile ? kColO1 : kColO0);
-    // P rows in smem: tile 0 row = lrow; tile 1 keeps only its 16 live rows (lane = lrow - 96)
-    uint8_t* p_base = smem + (tile ? kOffP1 : kOffP0);
-    const int p_block = tile ? kP1BlockBytes : kP0BlockBytes;
-    const int p_row = tile ? (lrow - 96) : lrow;
+    // P goes to TMEM (this thread's lane, 72 columns of packed bf16 pairs): tile 0 has its own columns, tile 1
+    // reuses the first 72 columns of its S tile.
+    const uint32_t p_addr = tmem_base + lane_addr + (tile ? kColP1 : kColP0);
+    uint64_t* const my_s_full = tile ? &meta->s1_full : &meta->s0_full;
     constexpr float kC = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) in the exp2 domain
 
     int prev_src = -1;
     float prev_inv = 0.f;
-    long long prev_item = 0;
+    int prev_b = 0, prev_head = 0;
     auto epilogue = [&](int n_prev) {
       mbar_wait(&meta->o_full, n_prev & 1);
       tc_fence_after_sync();
@@ -679,9 +726,8 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
       __syncwarp();
       if (lane == 0) mbar_arrive(&meta->o_free);
       if (valid && prev_src >= 0) {
-        const TcItem it = tc_decode(a, prev_item);
-        uint4* dst = reinterpret_cast<uint4*>(a.out + (static_cast<long long>(it.b) * a.tokens_per_batch + prev_src) * a.dim +
-                                              it.head * kHeadDim);
+        uint4* dst = reinterpret_cast<uint4*>(a.out + (static_cast<long long>(prev_b) * a.tokens_per_batch + prev_src) * a.dim +
+                                              prev_head * kHeadDim);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 u;
@@ -709,7 +755,8 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
       const int my_src = valid ? meta->src[st][row] : -1;
       const int my_grp = valid ? meta->grp[st][row] : 0;
       const int masked = meta->masked[st];
-      mbar_wait(&meta->s_full, n & 1);
+      const int cur_b = meta->batch[st], cur_head = meta->head[st];
+      mbar_wait(my_s_full, n & 1);
       tc_fence_after_sync();
       float sv[kTok];
       {
@@ -732,7 +779,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
       }
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&meta->s_free);  // S(n) is in registers: the next S may overwrite TMEM
+      if (lane == 0 && tile == 0) mbar_arrive(&meta->s0_free);  // S(n) is in registers: S(n+1) may overwrite it
       if (masked) {
         // 0 / -100 on the scaled logits == 0 / -800 on the raw q.k products (scale 1/8)
         const uint4* g16 = reinterpret_cast<const uint4*>(meta->grp[st]);
@@ -770,23 +817,30 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
       // P(n) may only replace P(n-1) once P V(n-1) has retired; that is what o_full(n-1) says.  Doing the
       // previous item's epilogue here keeps the tensor pipe busy with P V(n-1) / S(n+1) under this softmax.
       if (n > 0) epilogue(n - 1);
+      // P(n) -> TMEM.  tcgen05.st is warp-collective: every lane stores (rows >= 144 hold don't-care values whose
+      // accumulator rows are never read).  P0(n) may replace P0(n-1) because epilogue(n-1) above has waited for
+      // o_full(n-1), i.e. P V(n-1) has retired; P1(n) goes over S1(n), which this thread has already pulled out.
       {
-        const uint32_t prow = smem_u32(p_base) + p_row * kRowBytes;
+        uint32_t c0[32], c1[32], c2[8];
 #pragma unroll
-        for (int ch = 0; ch < kTok / 8; ++ch) {
-          const uint32_t addr = prow + (ch >> 3) * p_block + (((ch & 7) ^ (lrow & 7)) << 4);
-          if (valid)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * ch]), "r"(pk[4 * ch + 1]),
-                         "r"(pk[4 * ch + 2]), "r"(pk[4 * ch + 3])
-                         : "memory");
+        for (int j = 0; j < 32; ++j) {
+          c0[j] = pk[j];
+          c1[j] = pk[32 + j];
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c2[j] = pk[64 + j];
+        tmem_st_32x32b_x32(p_addr, c0);
+        tmem_st_32x32b_x32(p_addr + 32, c1);
+        tmem_st_32x32b_x8(p_addr + 64, c2);
+        tmem_st_wait();
       }
-      fence_proxy_async_smem();
+      tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&meta->p_full);
       prev_src = my_src;
       prev_inv = 1.f / sum;
-      prev_item = blockIdx.x + static_cast<long long>(n) * gridDim.x;
+      prev_b = cur_b;
+      prev_head = cur_head;
     }
     if (cnt > 0) epilogue(cnt - 1);
   }

@@ -98,6 +98,15 @@ class AuroraEngine:
         self.cfg = cfg
         self.variant_args = dict(variant_args or {})  # wave: density_vars / angle_vars (aurora.py:816-824)
         self.shard_group = None  # torch.distributed group used by forward(..., sharded=True)
+        # transport of the halo exchange of a sharded forecast: "peer" = kernels writing into the neighbours' memory
+        # over NVLink inside the step's graph (sharding.PeerHalo), "nccl" = NCCL send / recv between graph segments,
+        # "auto" = peer whenever there is more than one rank
+        self.halo_mode = "auto"
+        self._peer: Optional["sharding.PeerHalo"] = None
+        # stage-level taps for parity tests: when set to a dict, `_run` stores fp32 copies of the encoder output and
+        # of the residual stream after every Swin block / patch merge / patch split under the reference's module names
+        self.taps: Optional[dict] = None
+        self.encoding_device: Optional[str] = None  # where pos / scale encodings are evaluated (None = model device)
         self.use_cuda_graph = False  # replay the step from a captured CUDA graph (outputs become static buffers)
         self._graphs: dict = {}
         self._capture: Optional[dict] = None  # state of a running segmented graph capture (see _exchange)
@@ -274,7 +283,15 @@ class AuroraEngine:
         d0 = self.cfg.embed_dim
         lat_h = (host[0] if host is not None else lat).detach().float().cpu()
         lon_h = (host[1] if host is not None else lon).detach().float().cpu()
-        pos, scale = E.pos_scale_encodings(d0, lat_h, lon_h, self.cfg.patch_size)
+        # WHERE the encodings are evaluated matters: the reference's patch area is a float32 difference of sines
+        # (posencoding.py:61-113), a cancellation whose last-bit noise is amplified to O(1) phase differences by the
+        # short wavelengths of the scale expansion, so its high-frequency scale features depend on the device's sin().
+        # The reference evaluates them on the model's device (the metadata moves with `batch.to(device)`,
+        # aurora.py:281, encoder.py:334-346); for a CUDA model that is the GPU, and so is this (same torch ops, same
+        # device: bit-identical to the reference there).  `encoding_device = "cpu"` reproduces the reference's CPU
+        # evaluation instead (the golden fixtures under tests/golden were written by the reference on the CPU).
+        enc_dev = torch.device(self.encoding_device) if self.encoding_device is not None else self.device
+        pos, scale = E.pos_scale_encodings(d0, lat_h.to(enc_dev), lon_h.to(enc_dev), self.cfg.patch_size)
         pos, scale = pos.to(self.device), scale.to(self.device)
         emb = cabi.linear_small(pos, self._f32("encoder.pos_embed.weight"), self._f32("encoder.pos_embed.bias"))
         emb = emb + cabi.linear_small(scale, self._f32("encoder.scale_embed.weight"), self._f32("encoder.scale_embed.bias"))
@@ -530,8 +547,11 @@ class AuroraEngine:
             # the GLOBAL window grid restricted to the windows touching this band (sharding.py)
             h_begin, h_global = slab
             c_, rows_, w_ = res
-            halo = self._buffer("bb.halo", (2, c_, sharding.HALO, w_ * 3 * d), torch.bfloat16)
-            self._exchange(qkv.view(c_, rows_, w_ * 3 * d), halo)
+            if self._peer is not None:
+                halo = self._peer.exchange(qkv.view(c_, rows_, w_ * 3 * d), sharding.HALO)
+            else:
+                halo = self._buffer("bb.halo", (2, c_, sharding.HALO, w_ * 3 * d), torch.bfloat16)
+                self._exchange(qkv.view(c_, rows_, w_ * 3 * d), halo)
             cabi.window_attention(qkv, att, batch=1, res=(c_, h_global, w_), window=ws, shift=ss, num_heads=heads,
                                   pad_qkv=pad, slab=(h_begin, rows_),
                                   halo_qkv=halo.view(2, c_, sharding.HALO, w_, 3 * d))
@@ -544,6 +564,32 @@ class AuroraEngine:
         sc2, sh2 = self._modulation(f"{prefix}.norm2", d)
         cabi.ln_mod_residual(y, scale=sc2, shift=sh2, residual=x_f32, out_f32=x_f32,
                              out_bf16=x_b16 if out_b16 is None else out_b16)
+
+    def _tap(self, name: str, t: torch.Tensor) -> None:
+        if self.taps is not None:
+            self.taps[name] = t.float().clone()
+
+    def _resolved_halo_mode(self) -> str:
+        if self.halo_mode not in ("auto", "peer", "nccl"):
+            raise ValueError(f"halo_mode must be 'auto', 'peer' or 'nccl', got {self.halo_mode!r}")
+        if self.halo_mode != "auto":
+            return self.halo_mode
+        import torch.distributed as dist
+
+        world = dist.get_world_size(self.shard_group) if dist.is_available() and dist.is_initialized() else 1
+        return "peer" if world > 1 else "nccl"
+
+    def _setup_halo_transport(self, all_res, plan) -> None:
+        """Create (collectively, once) the peer-memory transport when it is selected; `self._peer` is None for NCCL."""
+        if self._resolved_halo_mode() != "peer":
+            self._peer = None
+            return
+        d0 = self.cfg.embed_dim
+        side_max = max(r[0] * sharding.HALO * r[2] * 3 * d0 * 2**i * 2 for i, r in enumerate(all_res))
+        if self._peer is None or 2 * side_max > self._peer.region_bytes:
+            if self._capture is not None:
+                raise RuntimeError("the halo transport must be created before graph capture (run one eager step first)")
+            self._peer = sharding.PeerHalo(self.device, side_max, group=self.shard_group)
 
     def _exchange(self, local: torch.Tensor, halo: torch.Tensor) -> None:
         """The one exchange step of a sharded forecast (sharding.exchange_halo).  While a step is being captured
@@ -575,6 +621,8 @@ class AuroraEngine:
                 f"Patch height ({patch_res[0]}) must be divisible by ws[0] ({cfg.window_size[0]})")
         all_res, padded = stage_resolutions(patch_res, n_enc)
         lora_idx = self._lora_index(rollout_step)
+        if plan is not None:
+            self._setup_halo_transport(all_res, plan)
         # (first owned row, global height) of this rank's band at stage i, or None when not sharded
         slab_of = (lambda i: None) if plan is None else (lambda i: (plan.rows[i][0], plan.global_h[i]))
         l0 = x_f32.shape[0]
@@ -591,6 +639,7 @@ class AuroraEngine:
                 last0 = i == 0 and j == depth - 1 and n_enc > 1
                 self._block(f"backbone.encoder_layers.{i}.blocks.{j}", cur_f, cur_b, res, cfg.encoder_num_heads[i],
                             j % 2 == 1, lora_idx, out_b16=concat[:, d0:] if last0 else None, slab=slab_of(i))
+                self._tap(f"backbone.encoder_layers.{i}.blocks.{j}", cur_f)
             if i == 0 and (depth == 0 or n_enc == 1):
                 concat[:, d0:].copy_(cur_b)
             skips.append(cur_f)
@@ -606,6 +655,7 @@ class AuroraEngine:
                 nxt_b = self._buffer(f"bb.xb{i + 1}", (rows, 2 * dim), torch.bfloat16)
                 cabi.gemm(merged, self._bf16(f"{pre}.reduction.weight"), out_f32=nxt_f, out_bf16=nxt_b)
                 cur_f, cur_b = nxt_f, nxt_b
+                self._tap(pre, cur_f)
         for i in range(n_dec):
             index = n_dec - i - 1
             res = all_res[index]
@@ -616,6 +666,7 @@ class AuroraEngine:
                 self._block(f"backbone.decoder_layers.{i}.blocks.{j}", cur_f, cur_b, res, cfg.decoder_num_heads[i],
                             j % 2 == 1, lora_idx,
                             out_b16=concat[:, :d0] if (final and j == depth - 1) else None, slab=slab_of(index))
+                self._tap(f"backbone.decoder_layers.{i}.blocks.{j}", cur_f)
             if final and depth == 0:
                 concat[:, :d0].copy_(cur_b)
             if not final:
@@ -637,6 +688,7 @@ class AuroraEngine:
                 skip = skips[index - 1] if 0 < i < n_dec - 1 else None
                 cabi.gemm(sp, self._bf16(f"{pre}.lin2.weight"), residual=skip, out_f32=nxt_f, out_bf16=nxt_b)
                 cur_f, cur_b = nxt_f, nxt_b
+                self._tap(pre + ("+skip" if skip is not None else ""), cur_f)
         return concat
 
     # ------------------------------------------------------------------------------------------
@@ -939,9 +991,13 @@ class AuroraEngine:
                      for k in atmos_out_names}
         x_f32 = self._buffer("x0", (l_tot, d0), torch.float32)
         x_b16 = self._buffer("xb0", (l_tot, d0), torch.bfloat16)
+        if self._peer is not None:
+            self._peer.begin_step()
         for b in range(bsz):
             self._encode(batch, b, x_f32, x_b16, prep["abs_emb"][b], prep["posscale"])
+            self._tap("encoder", x_f32)
             xdec = self._backbone(x_f32, x_b16, patch_res, step, plan)
+            self._tap("backbone", xdec)
             self._decode(xdec, batch, b, patch_res, out_surf, out_atmos, step + 1)
         return out_surf, out_atmos
 
@@ -973,6 +1029,7 @@ class AuroraEngine:
             tuple((k, tuple(v.shape)) for k, v in batch.atmos_vars.items()),
             tuple(batch.metadata.atmos_levels), self._lora_index(step), min(step, 2), prep["sharded"],
             None if prep["plan"] is None else prep["plan"].rows,
+            self._resolved_halo_mode() if prep["sharded"] else None,
         )
         entry = self._graphs.get(sig)
         if entry is None:

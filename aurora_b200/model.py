@@ -91,6 +91,15 @@ class Aurora(nn.Module):
                 self._put(key, value)
         self._engine = None
         self._engine_sig = None
+        self.encoding_device: Optional[str] = None
+        """Device on which the position / scale encodings are evaluated; None = the parameters' device, which is what
+        the reference does (`batch.to(device)` moves lat / lon, aurora.py:281).  The reference's scale encoding is
+        device-dependent in its high-frequency features (float32 cancellation in the patch area, see
+        `AuroraEngine._pos_scale_embed`); set "cpu" to reproduce a reference that ran on the CPU."""
+        self.halo_mode = "auto"
+        """str: transport of the halo exchange in `forward(batch, sharded=True)`: "peer" (kernels storing into the
+        neighbouring GPUs' memory over NVLink, inside the step's CUDA graph), "nccl" (NCCL send / recv from the host),
+        "auto" = "peer" whenever more than one rank takes part."""
         self.use_cuda_graph = False
         """bool: replay each forward step from a captured CUDA graph (one capture per input signature).  Predictions
         are copies of the graph's static output buffers, so they stay valid like the reference's."""
@@ -138,6 +147,10 @@ class Aurora(nn.Module):
                                         variant_args=self._variant_args())
             self._engine_sig = sig
         self._engine.use_cuda_graph = bool(self.use_cuda_graph)
+        self._engine.halo_mode = self.halo_mode
+        if self._engine.encoding_device != self.encoding_device:
+            self._engine.encoding_device = self.encoding_device
+            self._engine._grid_cache = None
         return self._engine
 
     def forward(self, batch: Batch, sharded: bool = False) -> Batch:

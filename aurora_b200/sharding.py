@@ -6,6 +6,10 @@ attention is the only exchange step: before each attention call the ranks swap `
 projection with both neighbours (cyclic in latitude, because the shifted windows wrap), every rank then
 computes all windows touching its band (boundary windows are computed on both sides) and writes only its own
 rows — one send + one receive per neighbour per block, no all-reduce anywhere.
+
+Two transports for that exchange: `PeerHalo` — kernels of libaurora_b200.so that store the rows straight into the
+neighbours' memory over NVLink (CUDA IPC mappings) and hand over with release / acquire flags, all inside the
+step's CUDA graph — and `exchange_halo`, NCCL send / recv issued from the host between graph segments.
 """
 
 from __future__ import annotations
@@ -16,7 +20,7 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 
-__all__ = ["HALO", "SlabPlan", "plan_slabs", "exchange_halo", "gather_bands"]
+__all__ = ["HALO", "SlabPlan", "plan_slabs", "exchange_halo", "gather_bands", "PeerHalo"]
 
 HALO = 5  # window height 6: a window reaches at most 5 rows into a neighbouring band
 
@@ -104,3 +108,74 @@ def gather_bands(local: torch.Tensor, plans: list[SlabPlan], patch: int, dim: in
         pieces.append(torch.empty(shape, dtype=local.dtype, device=local.device))
     dist.all_gather(pieces, local.contiguous(), group=group)
     return torch.cat(pieces, dim=dim)
+
+
+class PeerHalo:
+    """Peer-memory transport of the halo exchange (protocol: `aurora_b200/csrc/halo.cu`).
+
+    One device buffer per rank — control words + two parity regions, each holding the rows above (side 0) and below
+    (side 1) the band — mapped by both neighbours through CUDA IPC.  `exchange` launches two kernels on the current
+    stream (push into the neighbours, wait for the neighbours' pushes) and returns this rank's halo `[2, C, halo, X]`;
+    nothing synchronises the host, so the calls can be captured in a CUDA graph.  Collective: every rank of `group`
+    must construct it, and call `exchange` the same number of times, in the same order.  A world of one rank is its own
+    neighbour (the band wraps onto itself), which exercises the same kernels without IPC.
+    """
+
+    def __init__(self, device: torch.device, side_bytes_max: int, group=None) -> None:
+        from aurora_b200 import cabi
+
+        self._cabi = cabi
+        self.group = group
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+        self.world, self.rank = world, rank
+        self.ctrl_bytes = cabi.AB_HALO_CTRL_BYTES
+        self.region_bytes = (2 * side_bytes_max + 255) // 256 * 256
+        self.buf = torch.zeros(self.ctrl_bytes + 2 * self.region_bytes, dtype=torch.uint8, device=device)
+        torch.cuda.synchronize(device)  # zero flags are in memory before any peer can write a round number
+        self.base = self.buf.data_ptr()
+        self._opened: dict[int, int] = {}
+        if world == 1:
+            self.above = self.below = self.base
+        else:
+            handle, offset = cabi.ipc_export(self.buf)
+            table: list = [None] * world
+            dist.all_gather_object(table, (handle, offset), group=group)
+
+            def peer_address(r: int) -> int:
+                if r == rank:
+                    return self.base
+                if r not in self._opened:
+                    self._opened[r] = cabi.ipc_open(table[r][0])
+                return self._opened[r] + table[r][1]
+
+            self.above = peer_address((rank - 1) % world)
+            self.below = peer_address((rank + 1) % world)
+            dist.barrier(group=group)  # every buffer is zeroed and mapped before the first push of any rank
+        self.index = 0
+
+    def begin_step(self) -> None:
+        """Parity restarts with every model step (a step has an even number of exchanges: 2 x sum(encoder depths))."""
+        assert self.index % 2 == 0, "odd number of halo exchanges in the previous step"
+        self.index = 0
+
+    def exchange(self, local: torch.Tensor, halo: int) -> torch.Tensor:
+        """`local` = this rank's band `[C, rows, X]` (contiguous, 2-byte elements).  Returns `[2, C, halo, X]`: the
+        `halo` rows above (index 0) and below (index 1) the band, valid once the stream reaches this point."""
+        cabi = self._cabi
+        c, rows, x = local.shape
+        side = c * halo * x * local.element_size()
+        if 2 * side > self.region_bytes or side % 16 != 0:
+            raise ValueError(f"halo of {side} bytes per side does not fit the {self.region_bytes}-byte region")
+        parity = self.index & 1
+        self.index += 1
+        region = self.ctrl_bytes + parity * self.region_bytes
+        cabi.halo_push(local, above_slot=self.above + region + side, below_slot=self.below + region,
+                       above_flag=self.above + 4, below_flag=self.below, ctrl=self.base, halo=halo)
+        cabi.halo_wait(self.base)
+        return self.buf[region:region + 2 * side].view(local.dtype).view(2, c, halo, x)
+
+    def close(self) -> None:
+        for base in self._opened.values():
+            self._cabi.ipc_close(base)
+        self._opened.clear()

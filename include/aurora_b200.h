@@ -140,6 +140,43 @@ int ab_window_index_map_host(const int32_t res[3], const int32_t window[3], cons
                              int32_t warped, int32_t* idx_out, uint8_t* group_out);
 
 /* ------------------------------------------------------------------------------------------------
+ * Latitude-sharded forecast: halo exchange through peer memory (NVLink / NVSwitch), no NCCL on the step path.
+ * The reference has no multi-GPU forward; the exchange exists because the shifted windows of
+ * swin3d.py:470-503 straddle the latitude bands.  See csrc/halo.cu for the protocol.
+ *
+ * Every rank allocates ONE device buffer (PyTorch owns it): AB_HALO_CTRL_BYTES of control words followed by
+ * 2 (parity) x 2 (side: 0 = rows above the band, 1 = rows below) slots of C * halo * row_bytes each, zero-filled
+ * once.  ab_ipc_export makes it mappable by the neighbouring processes, ab_ipc_open maps a neighbour's buffer
+ * (peer access is enabled on first use), ab_ipc_close unmaps it.
+ * ---------------------------------------------------------------------------------------------- */
+#define AB_IPC_HANDLE_BYTES 64
+#define AB_HALO_CTRL_BYTES 256
+
+/* handle: AB_IPC_HANDLE_BYTES bytes to send to the peer process; offset: of dev_ptr inside its allocation. */
+int ab_ipc_export(const void* dev_ptr, uint8_t* handle, uint64_t* offset);
+/* Map the allocation behind `handle` (exported by ANOTHER process on this node); *base_out + offset is the
+ * peer's dev_ptr in this process's address space. */
+int ab_ipc_open(const uint8_t* handle, void** base_out);
+int ab_ipc_close(void* base);
+
+typedef struct AbHaloPush {
+  const void* local;     /* this rank's band, [C, rows, row_bytes] contiguous (e.g. qkv: row_bytes = W * 3D * 2) */
+  void* above_slot;      /* PEER address: side-1 slot (current parity) of the rank above, [C, halo, row_bytes] */
+  void* below_slot;      /* PEER address: side-0 slot (current parity) of the rank below */
+  uint32_t* above_flag;  /* PEER address: control word 1 ("rows below me have landed") of the rank above */
+  uint32_t* below_flag;  /* PEER address: control word 0 ("rows above me have landed") of the rank below */
+  uint32_t* ctrl;        /* this rank's own control words (start of its buffer) */
+  int32_t c, rows, halo;
+  int32_t reserved_;
+  int64_t row_bytes;     /* multiple of 16 */
+} AbHaloPush;
+
+/* Copy the first / last `halo` rows of every level of `local` into the neighbours' slots and publish the round. */
+int ab_halo_push(const AbHaloPush* p, void* stream);
+/* Block the stream until BOTH neighbours' pushes of the current round have landed in this rank's slots. */
+int ab_halo_wait(uint32_t* ctrl, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * LayerNorm + modulation + residual, one pass over the token stream:
  *
  *   out[r, :] = residual[rr, :] + LN(y[r, :]) * scale + shift + add_rows[r % add_mod, :]

@@ -33,6 +33,9 @@ def _build(cfg_name, cls_name, seed):
     assert dataclasses.replace(model.config, autocast=False) == cfg   # only `autocast` differs (see fx.our_kwargs)
     extra = fx.air_extra_specs(cfg) if cls_name == "AuroraAirPollution" else ()
     model.load_state_dict(fx.make_state_dict(cfg, seed=seed, extra=extra), strict=True)
+    # goldens and the live oracle are CPU evaluations of the reference algorithm; its scale encoding depends on the
+    # device's sin() in the last bit (see AuroraEngine._pos_scale_embed), so evaluate the encodings where they did
+    model.encoding_device = "cpu"
     return cfg, model.to("cuda").eval()
 
 

@@ -1,6 +1,10 @@
-"""Latitude-sharded forward (one forecast over 2 GPUs, NCCL halo exchange) against the single-GPU forward.
-Every per-row computation is independent of how rows are split over ranks, so the result must be identical.
-Needs >= 2 CUDA devices (skipped otherwise; run with `gpurun --gpus 2`)."""
+"""Latitude-sharded forward (ONE forecast over N GPUs) against the single-GPU forward, for both transports of the halo
+exchange: `peer` (kernels storing into the neighbours' memory over NVLink, CUDA IPC mappings, the whole step in ONE
+CUDA graph) and `nccl` (NCCL send / recv between graph segments).  Every per-row computation is independent of how
+rows are split over ranks, so the result must be IDENTICAL, bit for bit.
+
+The multi-process cases need >= 2 (>= 8) CUDA devices (skipped otherwise; `gpurun --gpus 2` / `--gpus 8`); the
+single-GPU case runs the peer kernels with the band as its own neighbour."""
 
 import os
 import socket
@@ -19,7 +23,7 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, h, w):
     import torch.distributed as dist
 
     import aurora_b200 as ab
@@ -32,48 +36,85 @@ def _worker(rank, world, port, q):
     model = ab.Aurora(**fx.our_kwargs(cfg))
     model.load_state_dict(fx.make_state_dict(cfg, seed=31))
     model = model.to(f"cuda:{rank}").eval()
-    # patch_res (4, 48, 64): full 144-token windows at all three stages, zero padding in W at stage 3
-    batch = fx.make_batch(cfg, 192, 256, levels=fx.LEVELS4, b=1, seed=31, rollout_step=1)
-    local = model.forward(batch, sharded=True)
-    plans = local.slab_plans
-    full_surf = {k: sharding.gather_bands(v, plans, cfg.patch_size) for k, v in local.surf_vars.items()}
-    full_atmos = {k: sharding.gather_bands(v, plans, cfg.patch_size) for k, v in local.atmos_vars.items()}
-    torch.cuda.synchronize()
-    ok, worst = True, 0.0
-    # the same sharded step replayed from graph segments (NCCL exchanges eager between them): identical bits
-    keep = {k: v.clone() for k, v in local.atmos_vars.items()}
-    model.use_cuda_graph = True
-    for _ in range(2):  # capture + replay, then replay only
-        again = model.forward(batch, sharded=True)
+    # full 144-token windows at all three stages, zero padding in W at stage 3
+    batch = fx.make_batch(cfg, h, w, levels=fx.LEVELS4, b=1, seed=31, rollout_step=1)
+    ref = model.forward(batch) if rank == 0 else None
+    ok, worst, notes = True, 0.0, []
+    for mode in ("nccl", "peer"):
+        model.halo_mode = mode
+        model.use_cuda_graph = False
+        local = model.forward(batch, sharded=True)
+        plans = local.slab_plans
+        full_surf = {k: sharding.gather_bands(v, plans, cfg.patch_size) for k, v in local.surf_vars.items()}
+        full_atmos = {k: sharding.gather_bands(v, plans, cfg.patch_size) for k, v in local.atmos_vars.items()}
         torch.cuda.synchronize()
-        ok = ok and all(torch.equal(again.atmos_vars[k], keep[k]) for k in keep)
-    model.use_cuda_graph = False
-    if rank == 0:
-        ref = model.forward(batch)
-        for grp, got in ((ref.surf_vars, full_surf), (ref.atmos_vars, full_atmos)):
-            for k, v in grp.items():
-                ok = ok and got[k].shape == v.shape
-                worst = max(worst, (got[k] - v).abs().max().item())
-        ok = ok and worst == 0.0
-    dist.barrier()
-    q.put((rank, ok, worst, [p.rows for p in plans]))
+        keep = {k: v.clone() for k, v in local.atmos_vars.items()}
+        # the same sharded step replayed from a CUDA graph: identical bits.  peer: ONE graph holds the whole step
+        # including the 12 exchanges; nccl: 13 graph segments with the exchanges issued eagerly between them
+        model.use_cuda_graph = True
+        for _ in range(3):  # capture + replay, then replays only
+            again = model.forward(batch, sharded=True)
+            torch.cuda.synchronize()
+            ok = ok and all(torch.equal(again.atmos_vars[k], keep[k]) for k in keep)
+        entry = next(e for sig, e in model._engine._graphs.items() if sig[-1] == mode)
+        n_graphs = sum(isinstance(i, torch.cuda.CUDAGraph) for i in entry["items"])
+        ok = ok and n_graphs == (1 if mode == "peer" else 13)
+        notes.append((mode, n_graphs))
+        if rank == 0:
+            for grp, got in ((ref.surf_vars, full_surf), (ref.atmos_vars, full_atmos)):
+                for k, v in grp.items():
+                    ok = ok and got[k].shape == v.shape
+                    worst = max(worst, (got[k] - v).abs().max().item())
+            ok = ok and worst == 0.0
+        dist.barrier()
+    q.put((rank, ok, worst, [p.rows for p in plans], notes))
     dist.destroy_process_group()
 
 
-def test_sharded_forward_equals_single_gpu():
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+@pytest.mark.parametrize("world,h,w", [(2, 192, 256), (8, 640, 256)])
+def test_sharded_forward_equals_single_gpu(world, h, w):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, h, w)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=600) for _ in procs)
+    res = sorted(q.get(timeout=900) for _ in procs)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    assert res[0][1], res
-    print("slabs:", res[0][3], "max |sharded - single| =", res[0][2])
+    assert all(r[1] for r in res), res
+    print(f"[sharded x{world}] slabs:", res[0][3][:2], "... max |sharded - single| =", res[0][2], res[0][4])
+
+
+def test_peer_halo_kernels_on_one_gpu():
+    """World size 1: the band is the whole grid and wraps onto itself, so the peer transport pushes into its own
+    buffer — the same push / flag / wait kernels, no IPC.  Eager and single-graph replay must equal the plain
+    (unsharded) forward bit for bit, on changing inputs."""
+    import aurora_b200 as ab
+
+    cfg = fx.CONFIGS["tiny_lora"]
+    model = ab.Aurora(**fx.our_kwargs(cfg))
+    model.load_state_dict(fx.make_state_dict(cfg, seed=17))
+    model = model.to("cuda").eval()
+    b1 = fx.make_batch(cfg, 192, 256, levels=fx.LEVELS4, b=1, seed=17, rollout_step=1)
+    b2 = fx.make_batch(cfg, 192, 256, levels=fx.LEVELS4, b=1, seed=18, rollout_step=1)
+    plain1 = {k: v.clone() for k, v in model.forward(b1).atmos_vars.items()}
+    plain2 = {k: v.clone() for k, v in model.forward(b2).atmos_vars.items()}
+    model.halo_mode = "peer"
+    e1 = model.forward(b1, sharded=True).atmos_vars
+    assert model._engine._peer is not None and model._engine._peer.world == 1
+    for k in plain1:
+        assert torch.equal(plain1[k], e1[k]), k
+    model.use_cuda_graph = True
+    g1 = model.forward(b1, sharded=True).atmos_vars
+    g2 = model.forward(b2, sharded=True).atmos_vars
+    g1b = model.forward(b1, sharded=True).atmos_vars
+    entry = next(e for sig, e in model._engine._graphs.items() if sig[-1] == "peer")
+    assert len(entry["items"]) == 1  # the whole step, exchanges included, is one graph
+    for k in plain1:
+        assert torch.equal(plain1[k], g1[k]) and torch.equal(plain2[k], g2[k]) and torch.equal(plain1[k], g1b[k]), k

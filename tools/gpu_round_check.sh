@@ -1,16 +1,41 @@
 #!/bin/bash
-# One gpurun call that re-validates the tree on a B200: smoke, GPU parity tests, the bench line and the ncu
-# metrics pass (launch list + DRAM traffic).  Everything lands in gpurun_out/.
+# One gpurun call that re-validates the tree on a B200; everything lands in gpurun_out/.  Sections (pick with $1,
+# default "smoke tests bench"): smoke | tests | bench | refarm | probe | ncu
 mkdir -p gpurun_out
+SECTIONS="${*:-smoke tests bench}"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/gpu.txt 2>&1
-nproc >> gpurun_out/gpu.txt
-( time timeout 300 python -c "import __graft_entry__ as g; g.smoke()" ) > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"
-( time timeout 1200 python -m pytest tests -m gpu -q --maxfail=8 -p no:cacheprovider ) > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
-tail -5 gpurun_out/pytest_gpu.log
-( time timeout 600 python bench.py ) > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
-cat gpurun_out/bench.json | cut -c1-600
-( time timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-    -k regex:'gemm|window_attention|ln_mod|patch|perceiver|linear_small' --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e ) > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?"
-wc -l gpurun_out/launches.csv
-tail -3 gpurun_out/ncu_bench.log | cut -c1-300
+nproc >> gpurun_out/gpu.txt; free -g | head -2 >> gpurun_out/gpu.txt
+for s in $SECTIONS; do
+case $s in
+smoke)
+  ( time timeout 300 python -c "import __graft_entry__ as g; g.smoke()" ) > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"
+  tail -2 gpurun_out/smoke.log | head -1 ;;
+tests)
+  ( time timeout 1500 python -m pytest tests -m gpu -q --maxfail=8 -p no:cacheprovider -s -rs ) > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+  grep -E "passed|failed|FAILED|SKIPPED" gpurun_out/pytest_gpu.log | tail -12
+  grep -A14 "full-size parity" gpurun_out/pytest_gpu.log | cut -c1-160 ;;
+bench)
+  ( time timeout 900 python bench.py ) > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+  cut -c1-900 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+  python - <<'E'
+import json
+for ln in open("gpurun_out/bench.json"):
+    if ln.startswith("{"):
+        d = json.loads(ln)
+        print("gpu_reference:", json.dumps(d.get("gpu_reference"))[:700])
+        print("cpu_baseline:", json.dumps(d.get("cpu_baseline"))[:700])
+E
+  ;;
+refarm)
+  ( time timeout 1200 python bench.py --impl reference --steps 4 --warmup 1 ) > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "refarm rc=$?"
+  cut -c1-1200 gpurun_out/bench_ref.json ;;
+probe)
+  ( time timeout 300 python experimental/probe_attn_x1.py ) > gpurun_out/probe_attn_x1.log 2>&1; echo "probe rc=$?"
+  tail -12 gpurun_out/probe_attn_x1.log | cut -c1-400 ;;
+ncu)
+  ( time timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+      -k regex:'gemm|window_attention|ln_mod|patch|perceiver|linear_small|halo' --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-gpu-reference ) > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?"
+  wc -l gpurun_out/launches.csv; tail -3 gpurun_out/ncu_bench.log | cut -c1-300 ;;
+esac
+done

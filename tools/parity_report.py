@@ -15,6 +15,7 @@ out = {}
 for name, (cfg_name, cls_name, h, w, levels, bsz, step, seed) in MODEL_CASES.items():
     cfg = fx.CONFIGS[cfg_name]
     model = getattr(ab, cls_name)(**fx.our_kwargs(cfg, cls_name))
+    model.encoding_device = "cpu"  # goldens are CPU evaluations of the reference
     extra = fx.air_extra_specs(cfg) if cls_name == "AuroraAirPollution" else ()
     model.load_state_dict(fx.make_state_dict(cfg, seed=seed, extra=extra))
     model = model.to("cuda")
