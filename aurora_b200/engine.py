@@ -109,6 +109,7 @@ class AuroraEngine:
         self.encoding_device: Optional[str] = None  # where pos / scale encodings are evaluated (None = model device)
         self.use_cuda_graph = False  # replay the step from a captured CUDA graph (outputs become static buffers)
         self._graphs: dict = {}
+        self.replayed_launches = 0  # kernels of libaurora_b200.so launched by graph replays (ab_launch_count sees only captures)
         self._capture: Optional[dict] = None  # state of a running segmented graph capture (see _exchange)
         self.variant = variant
         some = next(iter(params.values()))
@@ -871,11 +872,6 @@ class AuroraEngine:
     def _prepare(self, batch: Batch, sharded: bool) -> dict:
         cfg = self.cfg
         slot = host_ll = None
-        if not sharded and self._is_pinned_host_batch(batch):
-            host_ll = (batch.metadata.lat, batch.metadata.lon)
-            batch, slot = self._upload_pinned(batch)  # full fields go up first (one DMA each); crop happens on the device
-        batch = batch.type(torch.float32)
-        batch = batch.crop(patch_size=cfg.patch_size)
         plans = plan = None
         if sharded:
             import torch.distributed as dist
@@ -883,8 +879,21 @@ class AuroraEngine:
             world = dist.get_world_size(self.shard_group) if dist.is_initialized() else 1
             rank = dist.get_rank(self.shard_group) if dist.is_initialized() else 0
             h_img = batch.spatial_shape[0]
-            plans = sharding.plan_slabs(h_img // cfg.patch_size, len(cfg.encoder_depths), world)
-            plan = plans[rank]
+            h_img -= h_img % cfg.patch_size if h_img % cfg.patch_size == 1 else 0  # Batch.crop (batch.py:149-163)
+            plans = plan_cache = sharding.plan_slabs(h_img // cfg.patch_size, len(cfg.encoder_depths), world)
+            plan = plan_cache[rank]
+        if self._is_pinned_host_batch(batch):
+            # full fields (one DMA each; the crop happens on the device) or, sharded, only this rank's latitude band
+            band = None if plan is None else plan.image_rows(cfg.patch_size)
+            lat_h = batch.metadata.lat
+            if band is not None:
+                lat_h = lat_h[band[0]:band[0] + band[1]]
+            host_ll = (lat_h, batch.metadata.lon)
+            batch, slot = self._upload_pinned(batch, band)
+        batch = batch.type(torch.float32)
+        if slot is None or plan is None:
+            batch = batch.crop(patch_size=cfg.patch_size)
+        if sharded and slot is None:
             r0, nr = plan.image_rows(cfg.patch_size)
             cut = lambda v: v[..., r0:r0 + nr, :]  # noqa: E731
             lat = batch.metadata.lat
@@ -926,8 +935,11 @@ class AuroraEngine:
         return bool(ts) and all((not t.is_cuda) and t.dtype == torch.float32 and t.is_contiguous() and t.is_pinned()
                                 for t in ts)
 
-    def _upload_pinned(self, batch: Batch):
-        """Host -> device copy of a batch held in PINNED host memory, on a dedicated copy stream into one of two
+    def _upload_pinned(self, batch: Batch, rows: Optional[tuple] = None):
+        """`rows = (first image row, count)`: upload only that latitude band (a sharded forecast); every (H, W) plane
+        then contributes one contiguous block of `count * W` floats, one asynchronous DMA each.
+
+        Host -> device copy of a batch held in PINNED host memory, on a dedicated copy stream into one of two
         persistent device buffer sets.  The copies of this call do not queue behind the kernels of the previous
         step (they only wait for the step that last read the same buffer set, two calls ago), so from the second
         call on the upload runs under the previous step's compute.  The host waits for the copies before it
@@ -947,13 +959,23 @@ class AuroraEngine:
             for grp in ("surf_vars", "static_vars", "atmos_vars"):
                 out[grp] = {}
                 for k, v in getattr(batch, grp).items():
-                    key = (grp, k, tuple(v.shape))
+                    shape = tuple(v.shape) if rows is None else tuple(v.shape[:-2]) + (rows[1], v.shape[-1])
+                    key = (grp, k, shape, rows)
                     dst = slot["bufs"].get(key)
                     if dst is None:
-                        dst = slot["bufs"][key] = torch.empty(v.shape, dtype=torch.float32, device=self.device)
-                    dst.copy_(v, non_blocking=True)
+                        dst = slot["bufs"][key] = torch.empty(shape, dtype=torch.float32, device=self.device)
+                    if rows is None:
+                        dst.copy_(v, non_blocking=True)
+                    else:
+                        src_planes = v.view(-1, v.shape[-2], v.shape[-1])
+                        dst_planes = dst.view(-1, rows[1], v.shape[-1])
+                        for i in range(src_planes.shape[0]):
+                            dst_planes[i].copy_(src_planes[i, rows[0]:rows[0] + rows[1]], non_blocking=True)
                     out[grp][k] = dst
-            lat = batch.metadata.lat.to(self.device, non_blocking=True)
+            lat_h = batch.metadata.lat
+            if rows is not None:
+                lat_h = lat_h[rows[0]:rows[0] + rows[1]] if lat_h.dim() == 1 else lat_h[rows[0]:rows[0] + rows[1], :]
+            lat = lat_h.to(self.device, non_blocking=True)
             lon = batch.metadata.lon.to(self.device, non_blocking=True)
             done = torch.cuda.Event()
             done.record(cs)
@@ -1049,6 +1071,7 @@ class AuroraEngine:
             # segments share one memory pool; an unsharded step is a single segment.
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
+            launches0 = cabi.launch_count()
             with torch.cuda.stream(side):
                 cap = {"pool": torch.cuda.graph_pool_handle(), "items": [], "graph": torch.cuda.CUDAGraph()}
                 cap["graph"].capture_begin(pool=cap["pool"], capture_error_mode="thread_local")
@@ -1060,7 +1083,8 @@ class AuroraEngine:
                     self._capture = None
                 items = cap["items"] + [cap["graph"]]
             torch.cuda.current_stream().wait_stream(side)
-            entry = {"items": items, "prep": sprep, "outs": outs, "posscale_src": prep["posscale"]}
+            entry = {"items": items, "prep": sprep, "outs": outs, "posscale_src": prep["posscale"],
+                     "launches": cabi.launch_count() - launches0}
             self._graphs[sig] = entry
         sprep = entry["prep"]
         sb = sprep["batch"]
@@ -1078,6 +1102,7 @@ class AuroraEngine:
                 item.replay()
             else:
                 item()  # halo exchange between two graph segments
+        self.replayed_launches += entry["launches"]
         # hand out copies (0.3 GB device-to-device, ~0.1 ms): predictions must not alias the graph's static output
         # buffers, or `list(rollout(...))` would hold the last step's data in every entry
         out_surf, out_atmos = ({k: v.clone() for k, v in d.items()} for d in entry["outs"])

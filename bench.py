@@ -512,6 +512,7 @@ def main() -> None:
     # ---- device-resident throughput ----
     barrier()
     launches0 = cabi.launch_count()
+    replayed0 = model._engine.replayed_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clk = ClockSampler(local_rank)   # samples through BOTH timed regions (device-resident and end-to-end)
     clk.__enter__()
@@ -520,7 +521,8 @@ def main() -> None:
         pred = model.forward(dev_batch)
     e1.record()
     barrier()
-    launches = cabi.launch_count() - launches0
+    # kernels launched by this library in the timed region: eager launches + those replayed from captured graphs
+    launches = (cabi.launch_count() - launches0) + (model._engine.replayed_launches - replayed0)
     ms = e0.elapsed_time(e1) / args.steps
 
     # ---- end to end through the public API from pinned host memory ----
@@ -597,6 +599,8 @@ def main() -> None:
     n_g, t_g, f_g, b_g = agg("gemm")
     n_a, t_a, f_a, b_a = agg("window_attention")
     n_l, t_l, _, b_l = agg("ln_mod_residual")
+    n_hp, t_hp, _, b_hp = agg("halo_push")
+    n_hw, t_hw, _, _ = agg("halo_wait")
     peak_tf = pk["bf16_tflops_sustained"] or pk["bf16_tflops"]
     roofline = {
         "kernel": "gemm_bf16_tn_kernel (tcgen05)", "bound": "tensor",
@@ -624,6 +628,13 @@ def main() -> None:
             },
         },
     }
+    if n_hp:
+        roofline["others"]["halo_exchange"] = {
+            "bound": "nvlink", "exchanges_per_step": n_hp, "push_seconds_per_step": t_hp,
+            "push_achieved_gbs": b_hp / t_hp / 1e9 if t_hp else None, "nvlink_peak_gbs_per_direction": 900.0,
+            "bytes_sent_per_exchange": b_hp / n_hp, "wait_seconds_per_step": t_hw,
+            "note": "rank 0, one eager instrumented step: push = stores into both neighbours' memory over NVLink; wait = "
+                    "spinning until both neighbours' pushes landed (includes the ranks' skew)"}
 
     # ---- max over ranks (times); bytes moved are summed over ranks for a sharded forecast ----
     if distributed:

@@ -118,3 +118,28 @@ def test_peer_halo_kernels_on_one_gpu():
     assert len(entry["items"]) == 1  # the whole step, exchanges included, is one graph
     for k in plain1:
         assert torch.equal(plain1[k], g1[k]) and torch.equal(plain2[k], g2[k]) and torch.equal(plain1[k], g1b[k]), k
+
+
+def test_sharded_forward_from_pinned_host_memory_uploads_the_band():
+    """A batch in PINNED host memory takes the overlapped upload in sharded mode too: only the rank's latitude band goes
+    up, one DMA per (H, W) plane.  World size 1 (band = whole cropped grid, 33 -> 32 rows): same bits as the device path."""
+    import aurora_b200 as ab
+    from aurora_b200 import Batch
+
+    cfg = fx.CONFIGS["tiny_lora"]
+    model = ab.Aurora(**fx.our_kwargs(cfg))
+    model.load_state_dict(fx.make_state_dict(cfg, seed=23))
+    model = model.to("cuda").eval()
+    model.halo_mode = "peer"
+    batches = [fx.make_batch(cfg, 193, 256, levels=fx.LEVELS4, b=1, seed=50 + i, rollout_step=1) for i in range(3)]
+    want = [{k: v.clone() for k, v in model.forward(b, sharded=True).atmos_vars.items()} for b in batches]
+    pin = lambda d: {k: v.contiguous().pin_memory() for k, v in d.items()}  # noqa: E731
+    pinned = [Batch(pin(b.surf_vars), pin(b.static_vars), pin(b.atmos_vars), b.metadata) for b in batches]
+    torch.cuda.synchronize()
+    preds = [model.forward(b, sharded=True) for b in pinned]   # no sync in between: uploads overlap the previous step
+    torch.cuda.synchronize()
+    assert model._engine._h2d is not None
+    for p, w in zip(preds, want):
+        assert next(iter(p.surf_vars.values())).shape[-2:] == (192, 256)
+        for k in w:
+            assert torch.equal(p.atmos_vars[k], w[k]), k
