@@ -228,7 +228,7 @@ class AbWindowAttention(C.Structure):
         ("slab_h_rows", C.c_int32),
         ("slab_halo", C.c_int32),
         ("reserved_", C.c_int32),
-        ("halo_qkv", C.c_void_p),
+        ("halo_kv", C.c_void_p),
     ]
 
 
@@ -333,9 +333,9 @@ def window_index_map_host(res, window, shift, warped: bool = True):
 def window_attention(qkv: torch.Tensor, out: torch.Tensor, *, batch: int, res, window, shift, num_heads: int,
                      pad_qkv: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
                      warped: bool = True, slab: Optional[tuple[int, int]] = None,
-                     halo_qkv: Optional[torch.Tensor] = None) -> None:
+                     halo_kv: Optional[torch.Tensor] = None) -> None:
     """`slab=(h_begin, h_rows)`: qkv / out hold only those rows of the global grid `res` (latitude sharding);
-    `halo_qkv` is bf16 [2, C, halo, W, 3D] with the rows above / below the slab (cyclic)."""
+    `halo_kv` is bf16 [2, C, halo, W, 2D]: K | V of the rows above / below the slab (cyclic)."""
     assert qkv.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and qkv.is_contiguous() and out.is_contiguous()
     d = num_heads * 64
     tokens = batch * res[0] * res[1] * res[2] if slab is None else res[0] * slab[1] * res[2]
@@ -353,12 +353,12 @@ def window_attention(qkv: torch.Tensor, out: torch.Tensor, *, batch: int, res, w
     a.num_heads, a.head_dim, a.warped = num_heads, 64, int(warped)
     if slab is not None:
         a.slab_h_begin, a.slab_h_rows = int(slab[0]), int(slab[1])
-        if halo_qkv is not None:
-            assert halo_qkv.dtype == torch.bfloat16 and halo_qkv.is_contiguous() and halo_qkv.dim() == 5
-            assert halo_qkv.shape[0] == 2 and halo_qkv.shape[1] == res[0] and halo_qkv.shape[3] == res[2]
-            assert halo_qkv.shape[4] == 3 * d
-            a.slab_halo = halo_qkv.shape[2]
-            a.halo_qkv = ptr(halo_qkv)
+        if halo_kv is not None:
+            assert halo_kv.dtype == torch.bfloat16 and halo_kv.is_contiguous() and halo_kv.dim() == 5
+            assert halo_kv.shape[0] == 2 and halo_kv.shape[1] == res[0] and halo_kv.shape[3] == res[2]
+            assert halo_kv.shape[4] == 2 * d
+            a.slab_halo = halo_kv.shape[2]
+            a.halo_kv = ptr(halo_kv)
     nw, nt, _ = window_geometry(res, window, shift)
     with _Timed("window_attention", work=4.0 * batch * nw * num_heads * nt * nt * 64, nbytes=8.0 * tokens * d):
         check(lib().ab_window_attention(C.byref(a), _s()), "ab_window_attention")
@@ -470,9 +470,13 @@ class AbHaloPush(C.Structure):
         ("ctrl", C.c_void_p),
         ("c", C.c_int32),
         ("rows", C.c_int32),
-        ("halo", C.c_int32),
-        ("reserved_", C.c_int32),
-        ("row_bytes", C.c_int64),
+        ("w", C.c_int32),
+        ("slot_rows", C.c_int32),
+        ("rows_to_above", C.c_int32),
+        ("rows_to_below", C.c_int32),
+        ("src_tok_bytes", C.c_int64),
+        ("tok_off_bytes", C.c_int64),
+        ("tok_bytes", C.c_int64),
     ]
 
 
@@ -498,15 +502,20 @@ def ipc_close(base: int) -> None:
 
 
 def halo_push(local: torch.Tensor, *, above_slot: int, below_slot: int, above_flag: int, below_flag: int, ctrl: int,
-              halo: int) -> None:
-    """`local` [C, rows, X] contiguous (any 2-byte dtype); the slot / flag arguments are raw (peer) addresses."""
-    assert local.dim() == 3 and local.is_contiguous()
+              slot_rows: int, rows_to_above: int, rows_to_below: int, col_from: int = 0) -> None:
+    """`local` [C, rows, W, K] contiguous (2-byte elements); columns [col_from, K) of the first `rows_to_above` /
+    last `rows_to_below` rows go to the neighbours.  The slot / flag arguments are raw (peer) addresses."""
+    assert local.dim() == 4 and local.is_contiguous()
+    es = local.element_size()
     a = AbHaloPush()
     a.local = ptr(local)
     a.above_slot, a.below_slot, a.above_flag, a.below_flag, a.ctrl = above_slot, below_slot, above_flag, below_flag, ctrl
-    a.c, a.rows, a.halo = local.shape[0], local.shape[1], halo
-    a.row_bytes = local.shape[2] * local.element_size()
-    with _Timed("halo_push", nbytes=2.0 * a.c * halo * a.row_bytes):
+    a.c, a.rows, a.w = local.shape[0], local.shape[1], local.shape[2]
+    a.slot_rows, a.rows_to_above, a.rows_to_below = slot_rows, rows_to_above, rows_to_below
+    a.src_tok_bytes = local.shape[3] * es
+    a.tok_off_bytes = col_from * es
+    a.tok_bytes = (local.shape[3] - col_from) * es
+    with _Timed("halo_push", nbytes=float(a.c) * (rows_to_above + rows_to_below) * a.w * a.tok_bytes):
         check(lib().ab_halo_push(C.byref(a), _s()), "ab_halo_push")
 
 

@@ -13,9 +13,12 @@
 //                          [3] CTA completion counter of the running push (local)
 //     slots : bf16 [2 parities][2 sides][C][halo][X]   side 0 = rows above my band, side 1 = rows below
 //
-// ab_halo_push : every rank copies its FIRST `halo` rows into the rank above's side-1 slot and its LAST `halo` rows
-//                into the rank below's side-0 slot with plain 16-byte stores over NVLink, then the last CTA to finish
-//                publishes the new round number in both neighbours' flags (st.release.sys after __threadfence_system).
+// ab_halo_push : every rank copies its FIRST rows into the rank above's side-1 slot and its LAST rows into the rank
+//                below's side-0 slot with plain 16-byte stores over NVLink — only as many rows as that neighbour's
+//                windows reach into this band (0..halo, computed by both sides from the global geometry) and only the
+//                byte range of every token the neighbour reads (k | v of the qkv projection: a rank never needs its
+//                neighbours' queries) — then the last CTA to finish publishes the new round number in both
+//                neighbours' flags (st.release.sys after __threadfence_system).
 // ab_halo_wait : one warp spins (ld.acquire.sys) until both of MY flags reached my own round number.
 //
 // Both are ordinary kernels on the caller's stream, so the whole sharded step — 48 exchanges — is captured in ONE
@@ -32,14 +35,15 @@ constexpr int kHaloThreads = 256;
 constexpr int kCtrlFlagAbove = 0, kCtrlFlagBelow = 1, kCtrlRound = 2, kCtrlDone = 3;
 
 struct HaloPushArgs {
-  const uint4* src;       // local band [C, rows, X16] in 16-byte units
-  uint4* dst_above;       // rank above: its side-1 slot [C, halo, X16]
+  const uint4* src;       // local band [C, rows, W, src_tok16] in 16-byte units
+  uint4* dst_above;       // rank above: its side-1 slot [C, slot_rows, W, tok16]
   uint4* dst_below;       // rank below: its side-0 slot
   uint32_t* flag_above;   // rank above: its ctrl[kCtrlFlagBelow]
   uint32_t* flag_below;   // rank below: its ctrl[kCtrlFlagAbove]
   uint32_t* ctrl;         // local control words
-  int c, rows, halo;
-  long long x16;          // 16-byte units per row
+  int c, rows, slot_rows, w;
+  int rows_to_above, rows_to_below;
+  int src_tok16, off16, tok16;  // 16-byte units per source token, offset of the copied range, units copied per token
   unsigned total_ctas;
 };
 
@@ -56,22 +60,30 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __global__ void __launch_bounds__(kHaloThreads) halo_push_kernel(const HaloPushArgs a) {
   const int side = blockIdx.z;
   const int c = blockIdx.y;
-  const long long chunk = static_cast<long long>(a.halo) * a.x16;  // contiguous in src and dst
-  const long long row0 = side == 0 ? 0 : (a.rows - a.halo);
-  const uint4* src = a.src + (static_cast<long long>(c) * a.rows + row0) * a.x16;
-  uint4* dst = (side == 0 ? a.dst_above : a.dst_below) + static_cast<long long>(c) * chunk;
+  const int n = side == 0 ? a.rows_to_above : a.rows_to_below;
+  // side 0: my rows [0, n) are the rows just BELOW the rank above -> its side-1 slot rows [0, n)
+  // side 1: my rows [rows - n, rows) are the rows just ABOVE the rank below -> its side-0 slot rows [slot_rows - n, ..)
+  const long long src_row0 = side == 0 ? 0 : (a.rows - n);
+  const long long dst_row0 = side == 0 ? 0 : (a.slot_rows - n);
+  const uint4* src = a.src + (static_cast<long long>(c) * a.rows + src_row0) * a.w * a.src_tok16 + a.off16;
+  uint4* dst = (side == 0 ? a.dst_above : a.dst_below) + (static_cast<long long>(c) * a.slot_rows + dst_row0) * a.w * a.tok16;
+  const long long units = static_cast<long long>(n) * a.w * a.tok16;  // contiguous in dst, token-strided in src
   const long long stride = static_cast<long long>(gridDim.x) * kHaloThreads;
+  auto src_of = [&](long long i) -> const uint4* {
+    const long long tok = i / a.tok16;
+    return src + tok * a.src_tok16 + (i - tok * a.tok16);
+  };
   long long i = static_cast<long long>(blockIdx.x) * kHaloThreads + threadIdx.x;
   // 4 independent 16-byte loads in flight per thread: the stores cross NVLink, keep the pipe full
-  for (; i + 3 * stride < chunk; i += 4 * stride) {
-    const uint4 v0 = __ldg(src + i), v1 = __ldg(src + i + stride), v2 = __ldg(src + i + 2 * stride),
-                v3 = __ldg(src + i + 3 * stride);
+  for (; i + 3 * stride < units; i += 4 * stride) {
+    const uint4 v0 = __ldg(src_of(i)), v1 = __ldg(src_of(i + stride)), v2 = __ldg(src_of(i + 2 * stride)),
+                v3 = __ldg(src_of(i + 3 * stride));
     dst[i] = v0;
     dst[i + stride] = v1;
     dst[i + 2 * stride] = v2;
     dst[i + 3 * stride] = v3;
   }
-  for (; i < chunk; i += stride) dst[i] = __ldg(src + i);
+  for (; i < units; i += stride) dst[i] = __ldg(src_of(i));
 
   __threadfence_system();  // my stores are ordered before whatever this CTA's thread 0 publishes below
   __syncthreads();
@@ -185,9 +197,17 @@ extern "C" int ab_halo_push(const AbHaloPush* p, void* stream) {
   AB_CHECK_ARG(p != nullptr && p->local != nullptr && p->above_slot != nullptr && p->below_slot != nullptr &&
                    p->above_flag != nullptr && p->below_flag != nullptr && p->ctrl != nullptr,
                "ab_halo_push: null argument");
-  AB_CHECK_ARG(p->c > 0 && p->halo > 0 && p->rows >= p->halo && p->row_bytes > 0 && p->row_bytes % 16 == 0,
-               "ab_halo_push: bad shape c=%d rows=%d halo=%d row_bytes=%lld (rows >= halo, 16-byte rows)", p->c, p->rows,
-               p->halo, static_cast<long long>(p->row_bytes));
+  AB_CHECK_ARG(p->c > 0 && p->w > 0 && p->slot_rows > 0 && p->rows > 0 && p->rows_to_above >= 0 && p->rows_to_below >= 0 &&
+                   p->rows_to_above <= p->slot_rows && p->rows_to_below <= p->slot_rows &&
+                   p->rows_to_above <= p->rows && p->rows_to_below <= p->rows,
+               "ab_halo_push: bad shape c=%d rows=%d w=%d slot_rows=%d to_above=%d to_below=%d", p->c, p->rows, p->w,
+               p->slot_rows, p->rows_to_above, p->rows_to_below);
+  AB_CHECK_ARG(p->src_tok_bytes > 0 && p->tok_bytes > 0 && p->tok_off_bytes >= 0 &&
+                   p->tok_off_bytes + p->tok_bytes <= p->src_tok_bytes && p->src_tok_bytes % 16 == 0 &&
+                   p->tok_off_bytes % 16 == 0 && p->tok_bytes % 16 == 0,
+               "ab_halo_push: token byte range [%lld, +%lld) of %lld must be 16-byte granular",
+               static_cast<long long>(p->tok_off_bytes), static_cast<long long>(p->tok_bytes),
+               static_cast<long long>(p->src_tok_bytes));
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
   AB_CHECK_ARG(al16(p->local) && al16(p->above_slot) && al16(p->below_slot), "ab_halo_push: 16-byte alignment");
   HaloPushArgs a;
@@ -199,11 +219,18 @@ extern "C" int ab_halo_push(const AbHaloPush* p, void* stream) {
   a.ctrl = p->ctrl;
   a.c = p->c;
   a.rows = p->rows;
-  a.halo = p->halo;
-  a.x16 = p->row_bytes / 16;
-  const long long chunk = static_cast<long long>(p->halo) * a.x16;
-  // enough CTAs to keep ~900 GB/s of NVLink stores in flight, a multiple of the grid's other two dimensions
-  long long per = (chunk + 4ll * kHaloThreads - 1) / (4ll * kHaloThreads);
+  a.slot_rows = p->slot_rows;
+  a.w = p->w;
+  a.rows_to_above = p->rows_to_above;
+  a.rows_to_below = p->rows_to_below;
+  a.src_tok16 = static_cast<int>(p->src_tok_bytes / 16);
+  a.off16 = static_cast<int>(p->tok_off_bytes / 16);
+  a.tok16 = static_cast<int>(p->tok_bytes / 16);
+  const int nmax = p->rows_to_above > p->rows_to_below ? p->rows_to_above : p->rows_to_below;
+  const long long units = static_cast<long long>(nmax) * a.w * a.tok16;
+  // enough CTAs to keep ~900 GB/s of NVLink stores in flight (2 per SM over the whole grid); even when nothing is
+  // sent one CTA per (level, side) runs so that the round is published
+  long long per = (units + 4ll * kHaloThreads - 1) / (4ll * kHaloThreads);
   const long long cap = (2ll * sm_count() + 2ll * p->c - 1) / (2ll * p->c);
   if (per > cap) per = cap;
   if (per < 1) per = 1;

@@ -40,9 +40,9 @@ struct AttnArgs {
   long long tokens_per_batch;
   int box_rows;  // tc kernel: consecutive window-row tokens moved by one TMA box (0 = cp.async gather)
   // Latitude slab (multi-GPU sharding of one forecast): qkv / out hold only rows [h_begin, h_begin + h_rows) of the
-  // global (C, H, W) grid; `halo` rows above and below (cyclic in H) come from halo_qkv [2][C][halo][W][3D].
+  // global (C, H, W) grid; `halo` rows above and below (cyclic in H) come from halo_kv [2][C][halo][W][2D] (K | V columns only).
   int slab, h_begin, h_rows, halo, kh_begin, kh_count;
-  const __nv_bfloat16* halo_qkv;
+  const __nv_bfloat16* halo_kv;
 };
 
 __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc) {
@@ -599,14 +599,21 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
           const int src = meta->lsrc[st][t0];
           const uint32_t off = static_cast<uint32_t>(t0) * kRowBytes;
           if (src >= 0) {
-            const bool from_halo = (src & kHaloFlag) != 0;
-            const int grow = from_halo ? (src & ~kHaloFlag) : static_cast<int>(row_base + src);
-            const CUtensorMap* tm = from_halo ? &tmap_halo : &tmap_qkv;
             const int col = it.head * kHeadDim;
-            tma_load_2d(stage + off, tm, &meta->full[st], col, grow);
-            tma_load_2d(stage + kTileBytes + off, tm, &meta->full[st], col + a.dim, grow);
-            tma_load_2d(stage + 2 * kTileBytes + off, tm, &meta->full[st], col + 2 * a.dim, grow);
-            bytes += 3u * r * kRowBytes;
+            if (src & kHaloFlag) {
+              // a neighbour's row: only its K and V are here (its query belongs to the neighbour's own output rows;
+              // the Q slot keeps stale bytes, whose score / output rows are never stored)
+              const int grow = src & ~kHaloFlag;
+              tma_load_2d(stage + kTileBytes + off, &tmap_halo, &meta->full[st], col, grow);
+              tma_load_2d(stage + 2 * kTileBytes + off, &tmap_halo, &meta->full[st], col + a.dim, grow);
+              bytes += 2u * r * kRowBytes;
+            } else {
+              const int grow = static_cast<int>(row_base + src);
+              tma_load_2d(stage + off, &tmap_qkv, &meta->full[st], col, grow);
+              tma_load_2d(stage + kTileBytes + off, &tmap_qkv, &meta->full[st], col + a.dim, grow);
+              tma_load_2d(stage + 2 * kTileBytes + off, &tmap_qkv, &meta->full[st], col + 2 * a.dim, grow);
+              bytes += 3u * r * kRowBytes;
+            }
           }
         }
         if (g.nwindows * kTok != g.res[0] * g.res[1] * g.res[2]) {
@@ -633,9 +640,14 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
         const int t = idx >> 3, chunk = idx & 7;
         const int src = meta->lsrc[st][t];
         const uint32_t off = swz(t, chunk);
+        if (src >= 0 && (src & kHaloFlag)) {  // a neighbour's row: K | V only (row pitch 2D)
+          const __nv_bfloat16* pk = a.halo_kv + static_cast<long long>(src & ~kHaloFlag) * (2 * a.dim) + it.head * kHeadDim + chunk * 8;
+          cp_async_16(sk + off, pk);
+          cp_async_16(sv + off, pk + a.dim);
+          continue;
+        }
         const __nv_bfloat16* p;
         if (src < 0) p = a.pad_qkv + it.head * kHeadDim + chunk * 8;  // zero-padded token: bias
-        else if (src & kHaloFlag) p = a.halo_qkv + static_cast<long long>(src & ~kHaloFlag) * ld + it.head * kHeadDim + chunk * 8;
         else p = a.qkv + (row_base + src) * ld + it.head * kHeadDim + chunk * 8;
         cp_async_16(sq + off, p);
         cp_async_16(sk + off, p + a.dim);
@@ -941,15 +953,15 @@ extern "C" int ab_window_attention(const AbWindowAttention* p, void* stream) {
   a.halo = p->slab_halo;
   a.kh_begin = 0;
   a.kh_count = a.g.nwin[1];
-  a.halo_qkv = reinterpret_cast<const __nv_bfloat16*>(p->halo_qkv);
+  a.halo_kv = reinterpret_cast<const __nv_bfloat16*>(p->halo_kv);
   if (a.slab) {
     AB_CHECK_ARG(p->batch == 1, "ab_window_attention: a latitude slab needs batch == 1");
     AB_CHECK_ARG(a.g.ntok == tc::kTok && p->bias == nullptr,
                  "ab_window_attention: latitude slabs are supported for full 144-token windows only");
     AB_CHECK_ARG(a.h_begin >= 0 && a.h_begin < p->res[1] && a.h_rows <= p->res[1],
                  "ab_window_attention: bad slab rows [%d, +%d) of %d", a.h_begin, a.h_rows, p->res[1]);
-    AB_CHECK_ARG(a.h_rows == p->res[1] || (a.halo >= a.g.ws[1] - 1 && p->halo_qkv != nullptr),
-                 "ab_window_attention: a slab needs halo_qkv with at least %d halo rows", a.g.ws[1] - 1);
+    AB_CHECK_ARG(a.h_rows == p->res[1] || (a.halo >= a.g.ws[1] - 1 && p->halo_kv != nullptr),
+                 "ab_window_attention: a slab needs halo_kv with at least %d halo rows", a.g.ws[1] - 1);
     // window rows (cyclic range) that contain at least one owned source row
     const int nk = a.g.nwin[1], hh = p->res[1];
     int first = -1, count = 0;
@@ -1024,9 +1036,9 @@ extern "C" int ab_window_attention(const AbWindowAttention* p, void* stream) {
       const long long rows = a.slab ? static_cast<long long>(p->res[0]) * a.h_rows * p->res[2]
                                     : static_cast<long long>(p->batch) * a.tokens_per_batch;
       if (make_tmap_16bit_2d(&tq, p->qkv, rows, 3ll * a.dim, 3ll * a.dim, r, kHeadDim, false) == AB_OK) a.box_rows = r;
-      if (a.box_rows > 0 && a.slab && a.halo > 0 && a.halo_qkv != nullptr) {
+      if (a.box_rows > 0 && a.slab && a.halo > 0 && a.halo_kv != nullptr) {
         const long long hrows = 2ll * p->res[0] * a.halo * p->res[2];
-        if (make_tmap_16bit_2d(&th, p->halo_qkv, hrows, 3ll * a.dim, 3ll * a.dim, r, kHeadDim, false) != AB_OK)
+        if (make_tmap_16bit_2d(&th, p->halo_kv, hrows, 2ll * a.dim, 2ll * a.dim, r, kHeadDim, false) != AB_OK)
           a.box_rows = 0;
       }
     }

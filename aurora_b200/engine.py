@@ -103,6 +103,8 @@ class AuroraEngine:
         # "auto" = peer whenever there is more than one rank
         self.halo_mode = "auto"
         self._peer: Optional["sharding.PeerHalo"] = None
+        self._slab_cache: dict = {}
+        self._shard_plans = None
         # stage-level taps for parity tests: when set to a dict, `_run` stores fp32 copies of the encoder output and
         # of the residual stream after every Swin block / patch merge / patch split under the reference's module names
         self.taps: Optional[dict] = None
@@ -546,16 +548,16 @@ class AuroraEngine:
         else:
             # latitude band of a sharded forecast: swap HALO rows of qkv with both neighbours, then attend over
             # the GLOBAL window grid restricted to the windows touching this band (sharding.py)
-            h_begin, h_global = slab
+            h_begin, h_global, to_above, to_below = slab
             c_, rows_, w_ = res
+            qkv4 = qkv.view(c_, rows_, w_, 3 * d)
             if self._peer is not None:
-                halo = self._peer.exchange(qkv.view(c_, rows_, w_ * 3 * d), sharding.HALO)
+                halo = self._peer.exchange(qkv4, sharding.HALO, to_above[shifted], to_below[shifted], col_from=d)
             else:
-                halo = self._buffer("bb.halo", (2, c_, sharding.HALO, w_ * 3 * d), torch.bfloat16)
-                self._exchange(qkv.view(c_, rows_, w_ * 3 * d), halo)
+                halo = self._buffer("bb.halo", (2, c_, sharding.HALO, w_, 2 * d), torch.bfloat16)
+                self._exchange(qkv4, halo, col_from=d)
             cabi.window_attention(qkv, att, batch=1, res=(c_, h_global, w_), window=ws, shift=ss, num_heads=heads,
-                                  pad_qkv=pad, slab=(h_begin, rows_),
-                                  halo_qkv=halo.view(2, c_, sharding.HALO, w_, 3 * d))
+                                  pad_qkv=pad, slab=(h_begin, rows_), halo_kv=halo)
         cabi.gemm(att, wproj, bias=self._f32(f"{prefix}.attn.proj.bias"), out_bf16=y)
         sc1, sh1 = self._modulation(f"{prefix}.norm1", d)
         cabi.ln_mod_residual(y, scale=sc1, shift=sh1, residual=x_f32, out_f32=x_f32, out_bf16=x_b16)
@@ -565,6 +567,28 @@ class AuroraEngine:
         sc2, sh2 = self._modulation(f"{prefix}.norm2", d)
         cabi.ln_mod_residual(y, scale=sc2, shift=sh2, residual=x_f32, out_f32=x_f32,
                              out_bf16=x_b16 if out_b16 is None else out_b16)
+
+    def _slab_info(self, plan, i: int):
+        """Band geometry of stage `i` and what this rank's NEIGHBOURS need from it: `to_above[shifted]` = how many of
+        my first rows the rank above's windows reach, `to_below[shifted]` = how many of my last rows the rank below's
+        (`sharding.halo_needs` evaluated for the neighbours' bands; every rank derives it from the same plan)."""
+        key = (plan, i)
+        hit = self._slab_cache.get(key)
+        if hit is None:
+            h = plan.global_h[i]
+            wh = self.cfg.window_size[1]
+            start, cnt = plan.rows[i]
+            # neighbours' bands at this stage: cyclic, sizes follow from the plan of the whole world
+            plans = self._shard_plans
+            above, below = plans[(plan.rank - 1) % plan.world], plans[(plan.rank + 1) % plan.world]
+            to_above, to_below = [], []
+            for shifted in (False, True):
+                sh = wh // 2 if shifted else 0
+                to_above.append(min(cnt, sharding.halo_needs(h, wh, sh, *above.rows[i])[1]))
+                to_below.append(min(cnt, sharding.halo_needs(h, wh, sh, *below.rows[i])[0]))
+            hit = (start, h, tuple(to_above), tuple(to_below))
+            self._slab_cache[key] = hit
+        return hit
 
     def _tap(self, name: str, t: torch.Tensor) -> None:
         if self.taps is not None:
@@ -592,14 +616,14 @@ class AuroraEngine:
                 raise RuntimeError("the halo transport must be created before graph capture (run one eager step first)")
             self._peer = sharding.PeerHalo(self.device, side_max, group=self.shard_group)
 
-    def _exchange(self, local: torch.Tensor, halo: torch.Tensor) -> None:
+    def _exchange(self, local: torch.Tensor, halo: torch.Tensor, col_from: int = 0) -> None:
         """The one exchange step of a sharded forecast (sharding.exchange_halo).  While a step is being captured
         for graph replay the NCCL point-to-point calls stay OUTSIDE the graphs: the running graph segment is
         closed, the exchange runs eagerly and is remembered as a host callable, and a new segment is opened, so a
         replayed step is `graph, exchange, graph, exchange, ..., graph` (49 graph launches + 48 exchanges instead
         of ~530 host-side launches)."""
         def run():
-            sharding.exchange_halo(local, sharding.HALO, out=halo, group=self.shard_group)
+            sharding.exchange_halo(local, sharding.HALO, out=halo, group=self.shard_group, col_from=col_from)
 
         cap = self._capture
         if cap is None:
@@ -624,8 +648,9 @@ class AuroraEngine:
         lora_idx = self._lora_index(rollout_step)
         if plan is not None:
             self._setup_halo_transport(all_res, plan)
-        # (first owned row, global height) of this rank's band at stage i, or None when not sharded
-        slab_of = (lambda i: None) if plan is None else (lambda i: (plan.rows[i][0], plan.global_h[i]))
+        # (first owned row, global height, rows to send up / down in {unshifted, shifted} blocks) of this rank's band at
+        # stage i, or None when not sharded
+        slab_of = (lambda i: None) if plan is None else (lambda i: self._slab_info(plan, i))
         l0 = x_f32.shape[0]
         concat = self._buffer("bb.concat", (l0, 2 * d0), self.ed)  # decoder operand type
         skips: list[Optional[torch.Tensor]] = []
@@ -1015,6 +1040,7 @@ class AuroraEngine:
         x_b16 = self._buffer("xb0", (l_tot, d0), torch.bfloat16)
         if self._peer is not None:
             self._peer.begin_step()
+        self._shard_plans = prep["plans"]
         for b in range(bsz):
             self._encode(batch, b, x_f32, x_b16, prep["abs_emb"][b], prep["posscale"])
             self._tap("encoder", x_f32)

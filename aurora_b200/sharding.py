@@ -20,7 +20,7 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 
-__all__ = ["HALO", "SlabPlan", "plan_slabs", "exchange_halo", "gather_bands", "PeerHalo"]
+__all__ = ["HALO", "SlabPlan", "plan_slabs", "halo_needs", "exchange_halo", "gather_bands", "PeerHalo"]
 
 HALO = 5  # window height 6: a window reaches at most 5 rows into a neighbouring band
 
@@ -64,14 +64,49 @@ def plan_slabs(h0: int, n_stages: int, world: int) -> list[SlabPlan]:
     return plans
 
 
-def exchange_halo(local: torch.Tensor, halo: int, out: Optional[torch.Tensor] = None, group=None) -> torch.Tensor:
-    """`local` is one rank's band `[C, rows, X]` (X = W * channels, contiguous).  Returns `[2, C, halo, X]`:
-    index 0 = the `halo` rows just above the band (the previous rank's last rows), index 1 = the rows just
-    below (the next rank's first rows); bands are cyclic neighbours.  One send + one receive per neighbour."""
-    c, rows, x = local.shape
+def halo_needs(h: int, window_h: int, shift_h: int, h_begin: int, h_rows: int) -> tuple[int, int]:
+    """How many token rows ABOVE and BELOW the band `[h_begin, h_begin + h_rows)` (cyclic in the global height `h`) the
+    attention windows touching the band reach: `(rows_above, rows_below)`, each in `0 .. window_h - 1`.  Same geometry
+    as `csrc/window_index.cuh`: two-sided zero padding to a multiple of the window (front = pad // 2), cyclic shift of
+    the token grid, windows never wrap across the padded frame (swin3d.py:470-503).  A band that covers the whole grid
+    needs nothing."""
+    if h <= window_h:  # maybe_adjust_windows: one window over the whole axis, no shift
+        window_h, shift_h = h, 0
+    pad = (-h) % window_h
+    lo = pad // 2
+    above = below = 0
+    owned = lambda r: (r - h_begin) % h < h_rows  # noqa: E731
+    for kh in range((h + pad) // window_h):
+        rows = [(q + shift_h) % h for q in range(kh * window_h - lo, (kh + 1) * window_h - lo) if 0 <= q < h]
+        if not any(owned(r) for r in rows):
+            continue
+        for r in rows:
+            if owned(r):
+                continue
+            up = (h_begin - r) % h                 # 1 = the row just above the band
+            down = (r - (h_begin + h_rows)) % h + 1  # 1 = the row just below
+            if up <= down:
+                above = max(above, up)
+            else:
+                below = max(below, down)
+    return above, below
+
+
+def exchange_halo(local: torch.Tensor, halo: int, out: Optional[torch.Tensor] = None, group=None,
+                  col_from: int = 0) -> torch.Tensor:
+    """`local` is one rank's band `[C, rows, X]` (X = W * channels, contiguous) or `[C, rows, W, K]`, of which only the
+    columns `[col_from, K)` of every token are exchanged (k | v of a qkv projection).  Returns `[2, C, halo, X]`
+    (`[2, C, halo, W, K - col_from]`): index 0 = the `halo` rows just above the band (the previous rank's last rows),
+    index 1 = the rows just below (the next rank's first rows); bands are cyclic neighbours.  One send + one receive
+    per neighbour."""
+    c, rows = local.shape[:2]
     assert rows >= halo, f"band of {rows} rows cannot serve a {halo}-row halo"
+    if local.dim() == 4:
+        local = local[..., col_from:]
+    else:
+        assert col_from == 0
     if out is None:
-        out = torch.empty(2, c, halo, x, dtype=local.dtype, device=local.device)
+        out = torch.empty(2, c, halo, *local.shape[2:], dtype=local.dtype, device=local.device)
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     first = local[:, :halo].contiguous()
     last = local[:, rows - halo:].contiguous()
@@ -159,21 +194,27 @@ class PeerHalo:
         assert self.index % 2 == 0, "odd number of halo exchanges in the previous step"
         self.index = 0
 
-    def exchange(self, local: torch.Tensor, halo: int) -> torch.Tensor:
-        """`local` = this rank's band `[C, rows, X]` (contiguous, 2-byte elements).  Returns `[2, C, halo, X]`: the
-        `halo` rows above (index 0) and below (index 1) the band, valid once the stream reaches this point."""
+    def exchange(self, local: torch.Tensor, halo: int, rows_to_above: int, rows_to_below: int,
+                 col_from: int = 0) -> torch.Tensor:
+        """`local` = this rank's band `[C, rows, W, K]` (contiguous, 2-byte elements).  Sends columns `[col_from, K)`
+        of its first `rows_to_above` rows to the rank above and of its last `rows_to_below` rows to the rank below
+        (what THEIR windows reach into this band, `halo_needs`), and returns this rank's halo
+        `[2, C, halo, W, K - col_from]`: index 0 = rows above the band (the nearest ones valid, at the END of the
+        `halo` rows), index 1 = rows below (nearest first); valid once the stream reaches this point."""
         cabi = self._cabi
-        c, rows, x = local.shape
-        side = c * halo * x * local.element_size()
+        c, rows, w, k = local.shape
+        kk = k - col_from
+        side = c * halo * w * kk * local.element_size()
         if 2 * side > self.region_bytes or side % 16 != 0:
             raise ValueError(f"halo of {side} bytes per side does not fit the {self.region_bytes}-byte region")
         parity = self.index & 1
         self.index += 1
         region = self.ctrl_bytes + parity * self.region_bytes
         cabi.halo_push(local, above_slot=self.above + region + side, below_slot=self.below + region,
-                       above_flag=self.above + 4, below_flag=self.below, ctrl=self.base, halo=halo)
+                       above_flag=self.above + 4, below_flag=self.below, ctrl=self.base, slot_rows=halo,
+                       rows_to_above=rows_to_above, rows_to_below=rows_to_below, col_from=col_from)
         cabi.halo_wait(self.base)
-        return self.buf[region:region + 2 * side].view(local.dtype).view(2, c, halo, x)
+        return self.buf[region:region + 2 * side].view(local.dtype).view(2, c, halo, w, kk)
 
     def close(self) -> None:
         for base in self._opened.values():

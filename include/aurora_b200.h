@@ -112,13 +112,14 @@ typedef struct AbWindowAttention {
   int32_t warped;
   /* Latitude slab (one forecast sharded over GPUs along H; all zero = whole grid).  qkv / out then hold only the
    * token rows [slab_h_begin, slab_h_begin + slab_h_rows) of the GLOBAL (C, H, W) grid, level-major
-   * [C, slab_h_rows, W, .], batch must be 1; `halo_qkv` bf16 [2, C, slab_halo, W, 3*D] holds the slab_halo rows
-   * above ([0]: rows h_begin-halo .. h_begin-1) and below ([1]: rows h_end .. h_end+halo-1) the slab, cyclic in H
-   * (received from the neighbouring ranks).  Every window touching the slab is computed, only the slab's own
-   * rows are written.  slab_halo >= window[1] - 1 is required; full 144-token windows only. */
+   * [C, slab_h_rows, W, .], batch must be 1; `halo_kv` bf16 [2, C, slab_halo, W, 2*D] holds the K | V columns of
+   * the slab_halo rows above ([0]: rows h_begin-halo .. h_begin-1) and below ([1]: rows h_end .. h_end+halo-1) the
+   * slab, cyclic in H (received from the neighbouring ranks; queries of foreign rows are never needed, and only
+   * the rows that windows touching the slab actually reach have to be valid).  Every window touching the slab is
+   * computed, only the slab's own rows are written.  slab_halo >= window[1] - 1; full 144-token windows only. */
   int32_t slab_h_begin, slab_h_rows, slab_halo;
   int32_t reserved_;
-  const void* halo_qkv;
+  const void* halo_kv;
 } AbWindowAttention;
 
 int ab_window_attention(const AbWindowAttention* p, void* stream);
@@ -145,7 +146,7 @@ int ab_window_index_map_host(const int32_t res[3], const int32_t window[3], cons
  * swin3d.py:470-503 straddle the latitude bands.  See csrc/halo.cu for the protocol.
  *
  * Every rank allocates ONE device buffer (PyTorch owns it): AB_HALO_CTRL_BYTES of control words followed by
- * 2 (parity) x 2 (side: 0 = rows above the band, 1 = rows below) slots of C * halo * row_bytes each, zero-filled
+ * 2 (parity) x 2 (side: 0 = rows above the band, 1 = rows below) slots of C * halo * W * tok_bytes each, zero-filled
  * once.  ab_ipc_export makes it mappable by the neighbouring processes, ab_ipc_open maps a neighbour's buffer
  * (peer access is enabled on first use), ab_ipc_close unmaps it.
  * ---------------------------------------------------------------------------------------------- */
@@ -160,18 +161,22 @@ int ab_ipc_open(const uint8_t* handle, void** base_out);
 int ab_ipc_close(void* base);
 
 typedef struct AbHaloPush {
-  const void* local;     /* this rank's band, [C, rows, row_bytes] contiguous (e.g. qkv: row_bytes = W * 3D * 2) */
-  void* above_slot;      /* PEER address: side-1 slot (current parity) of the rank above, [C, halo, row_bytes] */
+  const void* local;     /* this rank's band, [C, rows, W, src_tok_bytes] contiguous (qkv: src_tok_bytes = 3D * 2) */
+  void* above_slot;      /* PEER address: side-1 slot (current parity) of the rank above, [C, slot_rows, W, tok_bytes] */
   void* below_slot;      /* PEER address: side-0 slot (current parity) of the rank below */
   uint32_t* above_flag;  /* PEER address: control word 1 ("rows below me have landed") of the rank above */
   uint32_t* below_flag;  /* PEER address: control word 0 ("rows above me have landed") of the rank below */
   uint32_t* ctrl;        /* this rank's own control words (start of its buffer) */
-  int32_t c, rows, halo;
-  int32_t reserved_;
-  int64_t row_bytes;     /* multiple of 16 */
+  int32_t c, rows, w;
+  int32_t slot_rows;     /* rows a slot holds per level (the halo capacity, window height - 1) */
+  int32_t rows_to_above; /* my FIRST rows the rank above needs: land in its slot rows [0, n) */
+  int32_t rows_to_below; /* my LAST rows the rank below needs: land in its slot rows [slot_rows - n, slot_rows) */
+  int64_t src_tok_bytes; /* bytes per token of `local` */
+  int64_t tok_off_bytes; /* byte range of every token that is sent: [tok_off_bytes, tok_off_bytes + tok_bytes) */
+  int64_t tok_bytes;     /* (k | v of the qkv projection: offset D * 2, length 2D * 2); all multiples of 16 */
 } AbHaloPush;
 
-/* Copy the first / last `halo` rows of every level of `local` into the neighbours' slots and publish the round. */
+/* Copy the first / last rows of every level of `local` into the neighbours' slots and publish the round. */
 int ab_halo_push(const AbHaloPush* p, void* stream);
 /* Block the stream until BOTH neighbours' pushes of the current round have landed in this rank's slots. */
 int ab_halo_wait(uint32_t* ctrl, void* stream);

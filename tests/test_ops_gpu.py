@@ -321,7 +321,8 @@ def _slab_views(full_qkv, res, d3, h0, rows, halo):
     idx_top = [(h0 - halo + i) % h for i in range(halo)]
     idx_bot = [(h0 + rows + i) % h for i in range(halo)]
     local = g[:, idx_own].contiguous().view(c * rows * w, d3)
-    halo_t = torch.stack((g[:, idx_top], g[:, idx_bot]), 0).contiguous()  # [2, C, halo, W, 3D]
+    d = d3 // 3
+    halo_t = torch.stack((g[:, idx_top], g[:, idx_bot]), 0)[..., d:].contiguous()  # [2, C, halo, W, 2D]: K | V only
     return local, halo_t, idx_own
 
 
@@ -345,9 +346,15 @@ def test_window_attention_latitude_slabs_equal_whole_grid(res, heads, splits, sh
     for r in range(len(splits) - 1):
         h0, rows = splits[r], splits[r + 1] - splits[r]
         local, halo_t, idx_own = _slab_views(qkv, res, 3 * d, h0, rows, halo)
+        # only the rows `halo_needs` names may be read: poison the others (a neighbour does not send them)
+        from aurora_b200 import sharding
+
+        above, below = sharding.halo_needs(h, WS0[1], ss0[1], h0, rows)
+        halo_t[0, :, : halo - above] = float("nan")
+        halo_t[1, :, below:] = float("nan")
         out = torch.full((c * rows * w, d), float("nan"), device=DEV, dtype=torch.bfloat16)
         cabi.window_attention(local, out, batch=1, res=res, window=WS0, shift=ss0, num_heads=heads, pad_qkv=pad,
-                              slab=(h0, rows), halo_qkv=halo_t)
+                              slab=(h0, rows), halo_kv=halo_t)
         torch.cuda.synchronize()
         want = full_g[:, idx_own].reshape(c * rows * w, d)
         assert torch.equal(out, want), (r, (out.float() - want.float()).abs().max().item())

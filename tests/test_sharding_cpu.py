@@ -79,3 +79,38 @@ def test_exchange_halo_gloo(world):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok in res), res
+
+
+@pytest.mark.parametrize("h,world", [(180, 8), (90, 8), (45, 8), (48, 2), (24, 2), (160, 8), (40, 8), (78, 3)])
+@pytest.mark.parametrize("shifted", [False, True])
+def test_halo_needs_cover_exactly_the_rows_the_windows_reach(h, world, shifted):
+    """`halo_needs` against the oracle's window gather map (oracle/windows.py, bit-exact vs the reference): for every
+    band, the rows of all windows that contain at least one owned row, minus the owned rows, must be exactly the
+    `above` rows just above plus the `below` rows just below the band (nearest-first, no gaps needed beyond them)."""
+    import numpy as np
+
+    from oracle import windows as W
+
+    ws0, c, w = (2, 6, 12), 2, 12
+    ss0 = (1, 3, 6) if shifted else (0, 0, 0)
+    idx, ws, ss, _ = W.window_gather_map((c, h, w), ws0, ss0)
+    rows_of_window = [set(((t // w) % h) for t in win if t >= 0) for win in np.asarray(idx)]
+    base, rem = divmod(h, world)
+    start = 0
+    for r in range(world):
+        cnt = base + (1 if r < rem else 0)
+        owned = set(range(start, start + cnt))
+        needed = set()
+        for rows in rows_of_window:
+            if rows & owned:
+                needed |= rows - owned
+        above, below = S.halo_needs(h, ws0[1], ss0[1], start, cnt)
+        assert 0 <= above < ws0[1] and 0 <= below < ws0[1]
+        got = {(start - 1 - i) % h for i in range(above)} | {(start + cnt + i) % h for i in range(below)}
+        assert needed <= got, (r, sorted(needed), sorted(got))
+        # tight: the farthest row on each side is really needed
+        if above:
+            assert (start - above) % h in needed
+        if below:
+            assert (start + cnt + below - 1) % h in needed
+        start += cnt
