@@ -458,16 +458,17 @@ __device__ __forceinline__ void tc_translate(const AttnArgs& a, int src, int* lo
     return;
   }
   *store_row = -1;
-  int dt = h - (a.h_begin - a.halo);
-  dt %= g.res[1];
-  if (dt < 0) dt += g.res[1];
-  if (dt < a.halo) {
-    *load_row = kHaloFlag | ((c * a.halo + dt) * g.res[2] + w);
+  // A foreign row is taken from the NEARER side of the band (ties: above) — the same rule as sharding.halo_needs, which
+  // decides which rows the neighbours send: on a small grid a row can be within reach both ways round the cyclic axis.
+  int up = (a.h_begin - h) % g.res[1];                 // 1 = the row just above the band
+  if (up < 0) up += g.res[1];
+  int down = (h - (a.h_begin + a.h_rows)) % g.res[1];  // 0 = the row just below
+  if (down < 0) down += g.res[1];
+  if (up <= down + 1) {
+    *load_row = kHaloFlag | ((c * a.halo + (a.halo - up)) * g.res[2] + w);  // host guarantees up <= halo
     return;
   }
-  int db = (h - (a.h_begin + a.h_rows)) % g.res[1];
-  if (db < 0) db += g.res[1];
-  *load_row = kHaloFlag | (((g.res[0] + c) * a.halo + db) * g.res[2] + w);  // host guarantees db < halo
+  *load_row = kHaloFlag | (((g.res[0] + c) * a.halo + down) * g.res[2] + w);  // host guarantees down < halo
 }
 
 // TMEM columns (all multiples of 16): S0 [0,144)  P0 [144,216)  O0 [224,288)  S1 [288,432) with P1 = [288,360)  O1 [432,496)

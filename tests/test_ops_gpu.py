@@ -327,7 +327,10 @@ def _slab_views(full_qkv, res, d3, h0, rows, halo):
 
 
 @pytest.mark.parametrize("res,heads,splits", [((4, 24, 24), 2, (0, 12, 24)), ((4, 45, 90), 2, (0, 12, 24, 36, 45)),
-                                              ((4, 36, 48), 4, (0, 8, 20, 36))])
+                                              ((4, 36, 48), 4, (0, 8, 20, 36)),
+                                              # 6-row bands of a 12-row grid: a foreign row is within reach BOTH ways
+                                              # round the cyclic axis; kernel and halo_needs must pick the same side
+                                              ((4, 12, 24), 2, (0, 6, 12))])
 @pytest.mark.parametrize("shifted", [False, True])
 def test_window_attention_latitude_slabs_equal_whole_grid(res, heads, splits, shifted):
     """Every rank's slab result must equal the corresponding rows of the whole-grid result bit for bit."""

@@ -23,30 +23,35 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, q, h, w):
+def _worker(rank, world, port, q, h, w, one_gpu=False):
     import torch.distributed as dist
 
     import aurora_b200 as ab
     from aurora_b200 import sharding
 
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    dev = 0 if one_gpu else rank
+    torch.cuda.set_device(dev)
+    if one_gpu:  # every rank is a process on the SAME GPU: gloo for the rendezvous, CUDA IPC between the processes
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    else:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     cfg = fx.CONFIGS["tiny_lora"]
     model = ab.Aurora(**fx.our_kwargs(cfg))
     model.load_state_dict(fx.make_state_dict(cfg, seed=31))
-    model = model.to(f"cuda:{rank}").eval()
+    model = model.to(f"cuda:{dev}").eval()
     # full 144-token windows at all three stages, zero padding in W at stage 3
     batch = fx.make_batch(cfg, h, w, levels=fx.LEVELS4, b=1, seed=31, rollout_step=1)
     ref = model.forward(batch) if rank == 0 else None
     ok, worst, notes = True, 0.0, []
-    for mode in ("nccl", "peer"):
+    for mode in (("peer",) if one_gpu else ("nccl", "peer")):
         model.halo_mode = mode
         model.use_cuda_graph = False
         local = model.forward(batch, sharded=True)
         plans = local.slab_plans
-        full_surf = {k: sharding.gather_bands(v, plans, cfg.patch_size) for k, v in local.surf_vars.items()}
-        full_atmos = {k: sharding.gather_bands(v, plans, cfg.patch_size) for k, v in local.atmos_vars.items()}
+        host = (lambda t: t.cpu()) if one_gpu else (lambda t: t)   # gloo gathers on the host
+        full_surf = {k: sharding.gather_bands(host(v), plans, cfg.patch_size) for k, v in local.surf_vars.items()}
+        full_atmos = {k: sharding.gather_bands(host(v), plans, cfg.patch_size) for k, v in local.atmos_vars.items()}
         torch.cuda.synchronize()
         keep = {k: v.clone() for k, v in local.atmos_vars.items()}
         # the same sharded step replayed from a CUDA graph: identical bits.  peer: ONE graph holds the whole step
@@ -61,10 +66,13 @@ def _worker(rank, world, port, q, h, w):
         ok = ok and n_graphs == (1 if mode == "peer" else 13)
         notes.append((mode, n_graphs))
         if rank == 0:
+            worst_mode = 0.0
             for grp, got in ((ref.surf_vars, full_surf), (ref.atmos_vars, full_atmos)):
                 for k, v in grp.items():
                     ok = ok and got[k].shape == v.shape
-                    worst = max(worst, (got[k] - v).abs().max().item())
+                    worst_mode = max(worst_mode, (got[k].to(v.device) - v).abs().max().item())
+            notes.append((mode, "max |sharded - single|", worst_mode))
+            worst = max(worst, worst_mode)
             ok = ok and worst == 0.0
         dist.barrier()
     q.put((rank, ok, worst, [p.rows for p in plans], notes))
@@ -89,6 +97,28 @@ def test_sharded_forward_equals_single_gpu(world, h, w):
         assert p.exitcode == 0
     assert all(r[1] for r in res), res
     print(f"[sharded x{world}] slabs:", res[0][3][:2], "... max |sharded - single| =", res[0][2], res[0][4])
+
+
+@pytest.mark.parametrize("world,h,w", [(2, 192, 256), (3, 240, 256)])
+def test_peer_halo_over_ipc_between_processes_on_one_gpu(world, h, w):
+    """The real multi-process protocol on a SINGLE GPU: `world` processes share cuda:0 (the driver time-slices their
+    contexts), rendezvous over gloo, map each other's halo buffers with CUDA IPC and run the sharded forward with the
+    peer transport — push / release-flag / acquire-wait kernels between processes, one CUDA graph per step.  Must equal
+    the unsharded forward bit for bit.  (NCCL refuses two ranks on one device, so only the peer transport runs here.)"""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, h, w, True)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=900) for _ in procs)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), res
+    print(f"[sharded x{world} on one GPU, IPC] max |sharded - single| =", res[0][2], res[0][4])
 
 
 def test_peer_halo_kernels_on_one_gpu():
