@@ -18,7 +18,7 @@ __all__ = [
     "lib", "AbError", "check", "ptr", "stream_ptr", "launch_count", "gemm", "window_attention", "window_geometry",
     "window_index_map", "ln_mod_residual", "patch_merge_ln", "patch_split_ln", "perceiver_attention",
     "linear_small", "patchify", "unpatchify", "AbFieldIn", "AbFieldOut", "ipc_export", "ipc_open", "ipc_close",
-    "halo_push", "halo_wait",
+    "halo_push", "halo_wait", "AbSwinBlock", "swin_block", "swin_block_workspace_bytes",
 ]
 
 ABI_VERSION = 2  # == AB_ABI_VERSION in include/aurora_b200.h
@@ -108,6 +108,8 @@ EXPORTS = [
     "ab_ipc_close",
     "ab_halo_push",
     "ab_halo_wait",
+    "ab_swin_block",
+    "ab_swin_block_workspace_bytes",
 ]
 AB_IPC_HANDLE_BYTES = 64
 AB_HALO_CTRL_BYTES = 256
@@ -522,3 +524,31 @@ def halo_push(local: torch.Tensor, *, above_slot: int, below_slot: int, above_fl
 def halo_wait(ctrl: int) -> None:
     with _Timed("halo_wait"):
         check(lib().ab_halo_wait(C.c_void_p(ctrl), _s()), "ab_halo_wait")
+
+
+# ---- whole-block entry point (csrc/block.cu) ----------------------------------------------------------------------
+class AbSwinBlock(C.Structure):
+    _fields_ = [
+        ("x_f32", C.c_void_p), ("x_b16", C.c_void_p), ("out_b16", C.c_void_p),
+        ("w_qkv", C.c_void_p), ("w_proj", C.c_void_p), ("w_fc1", C.c_void_p), ("w_fc2", C.c_void_p),
+        ("b_qkv", C.c_void_p), ("b_proj", C.c_void_p), ("b_fc1", C.c_void_p), ("b_fc2", C.c_void_p),
+        ("pad_qkv", C.c_void_p),
+        ("scale1", C.c_void_p), ("shift1", C.c_void_p), ("scale2", C.c_void_p), ("shift2", C.c_void_p),
+        ("workspace", C.c_void_p), ("halo_push", C.POINTER(AbHaloPush)), ("halo_kv", C.c_void_p),
+        ("dim", C.c_int32), ("hidden", C.c_int32), ("num_heads", C.c_int32),
+        ("res", C.c_int32 * 3), ("window", C.c_int32 * 3), ("shift", C.c_int32 * 3),
+        ("ld_out_b16", C.c_int32), ("out_b16_dtype", C.c_int32),
+        ("slab_h_begin", C.c_int32), ("slab_h_rows", C.c_int32), ("halo_rows", C.c_int32),
+        ("eps", C.c_float),
+    ]
+
+
+def swin_block_workspace_bytes(tokens: int, dim: int, hidden: int) -> int:
+    n = C.c_size_t()
+    check(lib().ab_swin_block_workspace_bytes(C.c_int64(tokens), dim, hidden, C.byref(n)), "ab_swin_block_workspace_bytes")
+    return int(n.value)
+
+
+def swin_block(desc: AbSwinBlock) -> None:
+    """One whole Swin3DTransformerBlock in place on the token stream (see include/aurora_b200.h)."""
+    check(lib().ab_swin_block(C.byref(desc), _s()), "ab_swin_block")

@@ -2,6 +2,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <unordered_map>
 #include <string.h>
 
 namespace ab {
@@ -42,8 +43,43 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
+// Tensor maps are pure functions of (base, shape, pitch, box, type): the engine launches the same ~700 GEMM / attention
+// operands every step from persistent buffers, so the encoded descriptors are kept (a plan cache keyed on the operand)
+// instead of calling cuTensorMapEncodeTiled three times per launch.
+namespace {
+struct TmapKey {
+  const void* base;
+  uint64_t rows, cols, ld;
+  uint32_t box_rows, box_cols, fp16;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+           box_cols == o.box_cols && fp16 == o.fp16;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = reinterpret_cast<uintptr_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    for (uint64_t v : {k.rows, k.cols, k.ld, static_cast<uint64_t>(k.box_rows) << 32 | k.box_cols, static_cast<uint64_t>(k.fp16)})
+      h = (h ^ v) * 0x100000001B3ull + (h >> 29);
+    return static_cast<size_t>(h);
+  }
+};
+std::mutex g_tmap_mutex;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+constexpr size_t kTmapCacheMax = 16384;
+}  // namespace
+
 int make_tmap_16bit_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                        uint32_t box_rows, uint32_t box_cols, bool fp16) {
+  const TmapKey key{base, rows, cols, ld, box_rows, box_cols, fp16 ? 1u : 0u};
+  {
+    std::lock_guard<std::mutex> lock(g_tmap_mutex);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *out = it->second;
+      return AB_OK;
+    }
+  }
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
@@ -65,6 +101,11 @@ int make_tmap_16bit_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64
     set_error("cuTensorMapEncodeTiled failed (CUresult %d) rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r,
               (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);
     return AB_ERR_CUDA;
+  }
+  {
+    std::lock_guard<std::mutex> lock(g_tmap_mutex);
+    if (g_tmap_cache.size() >= kTmapCacheMax) g_tmap_cache.clear();
+    g_tmap_cache.emplace(key, *out);
   }
   return AB_OK;
 }

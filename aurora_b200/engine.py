@@ -20,6 +20,7 @@ There is NO CPU path: tensors that are not on a CUDA device raise.
 
 from __future__ import annotations
 
+import ctypes
 import dataclasses
 from datetime import timedelta
 from typing import Optional
@@ -104,6 +105,7 @@ class AuroraEngine:
         self.halo_mode = "auto"
         self._peer: Optional["sharding.PeerHalo"] = None
         self._slab_cache: dict = {}
+        self.block_entry = True  # run Swin blocks through the whole-block entry point ab_swin_block
         self._shard_plans = None
         # stage-level taps for parity tests: when set to a dict, `_run` stores fp32 copies of the encoder output and
         # of the residual stream after every Swin block / patch merge / patch split under the reference's module names
@@ -537,6 +539,11 @@ class AuroraEngine:
         ws = tuple(self.cfg.window_size)
         ss = tuple(s // 2 for s in ws) if shifted else (0, 0, 0)
         wqkv, wproj = self._attn_weights(prefix, lora_idx)
+        if self.block_entry and cabi.PROFILE is None and (slab is None or self._peer is not None):
+            # one call into the library per block (ab_swin_block); the per-kernel path below is kept for per-kernel
+            # timing (bench.py's roofline leg) and for the NCCL halo transport, whose exchange is issued from Python
+            self._block_entry(prefix, x_f32, x_b16, res, heads, ws, ss, shifted, wqkv, wproj, out_b16, slab)
+            return
         qkv = self._buffer("bb.qkv", (l, 3 * d), torch.bfloat16)
         att = self._buffer("bb.att", (l, d), torch.bfloat16)
         y = self._buffer("bb.y", (l, d), torch.bfloat16)
@@ -593,6 +600,41 @@ class AuroraEngine:
     def _tap(self, name: str, t: torch.Tensor) -> None:
         if self.taps is not None:
             self.taps[name] = t.float().clone()
+
+    def _block_entry(self, prefix, x_f32, x_b16, res, heads, ws, ss, shifted, wqkv, wproj, out_b16, slab) -> None:
+        l, d = x_f32.shape
+        hidden = self._f32(f"{prefix}.mlp.fc1.bias").numel()
+        b = cabi.AbSwinBlock()
+        b.x_f32, b.x_b16 = x_f32.data_ptr(), x_b16.data_ptr()
+        if out_b16 is not None:
+            b.out_b16, b.ld_out_b16, b.out_b16_dtype = out_b16.data_ptr(), out_b16.stride(0), cabi._dt(out_b16)
+        b.w_qkv, b.w_proj = wqkv.data_ptr(), wproj.data_ptr()
+        b.w_fc1, b.w_fc2 = self._bf16(f"{prefix}.mlp.fc1.weight").data_ptr(), self._bf16(f"{prefix}.mlp.fc2.weight").data_ptr()
+        b.b_qkv, b.b_proj = self._f32(f"{prefix}.attn.qkv.bias").data_ptr(), self._f32(f"{prefix}.attn.proj.bias").data_ptr()
+        b.b_fc1, b.b_fc2 = self._f32(f"{prefix}.mlp.fc1.bias").data_ptr(), self._f32(f"{prefix}.mlp.fc2.bias").data_ptr()
+        b.pad_qkv = self._vec(f"{prefix}.pad_qkv", lambda: self._f32(f"{prefix}.attn.qkv.bias").to(torch.bfloat16)).data_ptr()
+        sc1, sh1 = self._modulation(f"{prefix}.norm1", d)
+        sc2, sh2 = self._modulation(f"{prefix}.norm2", d)
+        b.scale1, b.shift1, b.scale2, b.shift2 = sc1.data_ptr(), sh1.data_ptr(), sc2.data_ptr(), sh2.data_ptr()
+        nbytes = cabi.swin_block_workspace_bytes(l, d, hidden)
+        b.workspace = self._buffer("bb.ws", (nbytes,), torch.uint8).data_ptr()
+        b.dim, b.hidden, b.num_heads, b.eps = d, hidden, heads, 1e-5
+        b.window, b.shift = cabi._i3(ws), cabi._i3(ss)
+        keep = None
+        if slab is None:
+            b.res = cabi._i3(res)
+        else:
+            h_begin, h_global, to_above, to_below = slab
+            c_, rows_, w_ = res
+            b.res = cabi._i3((c_, h_global, w_))
+            b.slab_h_begin, b.slab_h_rows, b.halo_rows = h_begin, rows_, sharding.HALO
+            hp, halo = self._peer.descriptor((c_, rows_, w_, 3 * d), torch.bfloat16, sharding.HALO, to_above[shifted],
+                                             to_below[shifted], col_from=d)
+            keep = hp
+            b.halo_push = ctypes.pointer(hp)
+            b.halo_kv = halo.data_ptr()
+        cabi.swin_block(b)
+        del keep
 
     def _resolved_halo_mode(self) -> str:
         if self.halo_mode not in ("auto", "peer", "nccl"):

@@ -216,6 +216,29 @@ class PeerHalo:
         cabi.halo_wait(self.base)
         return self.buf[region:region + 2 * side].view(local.dtype).view(2, c, halo, w, kk)
 
+    def descriptor(self, shape: tuple, dtype: torch.dtype, halo: int, rows_to_above: int, rows_to_below: int,
+                   col_from: int = 0):
+        """The same exchange as a launch descriptor for `ab_swin_block` (which fills in the source pointer and issues
+        push + wait between the qkv projection and the attention): returns `(AbHaloPush, halo view)` and advances the
+        parity exactly like `exchange`."""
+        cabi = self._cabi
+        c, rows, w, k = shape
+        es = torch.empty((), dtype=dtype).element_size()
+        kk = k - col_from
+        side = c * halo * w * kk * es
+        if 2 * side > self.region_bytes or side % 16 != 0:
+            raise ValueError(f"halo of {side} bytes per side does not fit the {self.region_bytes}-byte region")
+        parity = self.index & 1
+        self.index += 1
+        region = self.ctrl_bytes + parity * self.region_bytes
+        a = cabi.AbHaloPush()
+        a.above_slot, a.below_slot = self.above + region + side, self.below + region
+        a.above_flag, a.below_flag, a.ctrl = self.above + 4, self.below, self.base
+        a.c, a.rows, a.w, a.slot_rows = c, rows, w, halo
+        a.rows_to_above, a.rows_to_below = rows_to_above, rows_to_below
+        a.src_tok_bytes, a.tok_off_bytes, a.tok_bytes = k * es, col_from * es, kk * es
+        return a, self.buf[region:region + 2 * side].view(dtype).view(2, c, halo, w, kk)
+
     def close(self) -> None:
         for base in self._opened.values():
             self._cabi.ipc_close(base)

@@ -215,6 +215,51 @@ typedef struct AbLnModResidual {
 
 int ab_ln_mod_residual(const AbLnModResidual* p, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * One whole Swin3DTransformerBlock (swin3d.py:440-509) in place on the token stream: qkv projection, [halo
+ * exchange of a latitude slab], shifted-window attention, output projection, adaLN + residual, MLP (erf GELU),
+ * adaLN + residual — 8 to 10 launches of this library on `stream`.  See csrc/block.cu.
+ *   x_f32   f32 [tokens, dim]   residual stream, updated in place
+ *   x_b16   bf16 [tokens, dim]  16-bit copy of the stream (A operand of qkv / fc1), rewritten after each sub-layer
+ *   out_b16 optional: where the 16-bit copy of the block OUTPUT goes instead of x_b16 (leading dimension
+ *           ld_out_b16, AB_DT_* out_b16_dtype), e.g. one half of the decoder's [x | skip] concatenation
+ *   weights bf16 in nn.Linear layout [out, in] (LoRA merged by the caller), biases / modulation vectors f32;
+ *           scale = scale_bias + scale(c), shift = shift(c) of AdaptiveLayerNorm (film.py:48-49)
+ *   workspace: ab_swin_block_workspace_bytes(tokens, dim, hidden) bytes, 256-byte aligned, owned by the caller
+ *   res / window / shift as in AbWindowAttention.  Latitude slab (slab_h_rows > 0): `res[1]` is the GLOBAL height,
+ *   the stream holds rows [slab_h_begin, +slab_h_rows); halo_kv as in AbWindowAttention; halo_push (optional) is
+ *   the peer-memory exchange to run between the projection and the attention (its `local` is filled in here).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct AbSwinBlock {
+  float* x_f32;
+  void* x_b16;
+  void* out_b16;
+  const void* w_qkv;
+  const void* w_proj;
+  const void* w_fc1;
+  const void* w_fc2;
+  const float* b_qkv;
+  const float* b_proj;
+  const float* b_fc1;
+  const float* b_fc2;
+  const void* pad_qkv;   /* bf16 [3 * dim]: the qkv bias, q | k | v of zero-padded tokens */
+  const float* scale1;
+  const float* shift1;
+  const float* scale2;
+  const float* shift2;
+  void* workspace;
+  const struct AbHaloPush* halo_push;
+  const void* halo_kv;
+  int32_t dim, hidden, num_heads;
+  int32_t res[3], window[3], shift[3];
+  int32_t ld_out_b16, out_b16_dtype;
+  int32_t slab_h_begin, slab_h_rows, halo_rows;
+  float eps;
+} AbSwinBlock;
+
+int ab_swin_block_workspace_bytes(int64_t tokens, int32_t dim, int32_t hidden, size_t* bytes);
+int ab_swin_block(const AbSwinBlock* b, void* stream);
+
 /* PatchMerging3D front half (swin3d.py:526-553): x f32 [batch, C, H, W, D] -> zero pad H, W to even at
  * the bottom / right -> 2x2 gather with feature order (h w D) -> LayerNorm(4D) with affine gamma/beta
  * -> bf16 [batch*C*ceil(H/2)*ceil(W/2), 4D], the A operand of `reduction` (ab_gemm_bf16). */

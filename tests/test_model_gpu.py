@@ -45,9 +45,18 @@ def test_forward_matches_reference_golden(name):
     cfg, model = _build(cfg_name, cls_name, seed)
     batch = fx.case_inputs(MODEL_CASES[name])[2]
     wave = cls_name == "AuroraWave"
+    eng = model._get_engine()
+    eng.taps = {}
     pred = model.forward(batch)
     torch.cuda.synchronize()
+    taps, eng.taps = eng.taps, None
     gold = np.load(GOLD / f"model_{name}.npz")
+    # stage-level taps of the reference (forward hooks on its encoder / backbone, float64): the engine's encoder output
+    # and decoder input for the LAST batch element
+    for tap in ("encoder", "backbone"):
+        ref_tap = torch.from_numpy(gold[f"tap.{tap}"])[-1]
+        err = fx.rel_mean_abs(taps[tap].cpu(), ref_tap)
+        assert err < 5e-3, (name, tap, err)
     assert pred.metadata.rollout_step == int(gold["meta.rollout_step"])
     assert pred.metadata.time[0].timestamp() == float(gold["meta.time0"])
     worst = 0.0
@@ -253,3 +262,27 @@ def test_graph_rollout_yields_independent_predictions(lora_mode):
         for i, p in enumerate(preds):
             for k, v in p.atmos_vars.items():
                 assert torch.equal(v, eager[i][k]), (i, k)
+
+
+def test_whole_block_entry_point_equals_the_per_kernel_path():
+    """`ab_swin_block` (one C call per Swin block: csrc/block.cu) issues exactly the launches the per-kernel path issues
+    from Python — same bits, fewer calls; also with the skip-concatenation destination (fp16 halves of the decoder
+    input) and for a zero-padded stage."""
+    from aurora_b200 import cabi
+
+    cfg, model = _build("tiny_lora", "Aurora", 29)
+    batch = fx.make_batch(cfg, 192, 256, levels=fx.LEVELS4, b=1, seed=29, rollout_step=1)
+    eng = model._get_engine()
+    assert eng.block_entry
+    n0 = cabi.launch_count()
+    fused = model.forward(batch)
+    n_fused = cabi.launch_count() - n0
+    eng.block_entry = False
+    n0 = cabi.launch_count()
+    plain = model.forward(batch)
+    n_plain = cabi.launch_count() - n0
+    assert n_fused == n_plain  # same kernels, only the host-side call count differs
+    for k in plain.atmos_vars:
+        assert torch.equal(plain.atmos_vars[k], fused.atmos_vars[k]), k
+    for k in plain.surf_vars:
+        assert torch.equal(plain.surf_vars[k], fused.surf_vars[k]), k
