@@ -18,7 +18,8 @@ __all__ = [
     "lib", "AbError", "check", "ptr", "stream_ptr", "launch_count", "gemm", "window_attention", "window_geometry",
     "window_index_map", "ln_mod_residual", "patch_merge_ln", "patch_split_ln", "perceiver_attention",
     "linear_small", "patchify", "unpatchify", "AbFieldIn", "AbFieldOut", "ipc_export", "ipc_open", "ipc_close",
-    "halo_push", "halo_wait", "AbSwinBlock", "swin_block", "swin_block_workspace_bytes",
+    "halo_push", "halo_wait", "AbSwinBlock", "swin_block", "swin_block_workspace_bytes", "gemm_ln_supported",
+    "gemm_ln_residual",
 ]
 
 ABI_VERSION = 2  # == AB_ABI_VERSION in include/aurora_b200.h
@@ -110,6 +111,8 @@ EXPORTS = [
     "ab_halo_wait",
     "ab_swin_block",
     "ab_swin_block_workspace_bytes",
+    "ab_gemm_ln_supported",
+    "ab_gemm_ln_residual",
 ]
 AB_IPC_HANDLE_BYTES = 64
 AB_HALO_CTRL_BYTES = 256
@@ -539,7 +542,7 @@ class AbSwinBlock(C.Structure):
         ("res", C.c_int32 * 3), ("window", C.c_int32 * 3), ("shift", C.c_int32 * 3),
         ("ld_out_b16", C.c_int32), ("out_b16_dtype", C.c_int32),
         ("slab_h_begin", C.c_int32), ("slab_h_rows", C.c_int32), ("halo_rows", C.c_int32),
-        ("eps", C.c_float),
+        ("eps", C.c_float), ("fuse_ln", C.c_int32),
     ]
 
 
@@ -552,3 +555,47 @@ def swin_block_workspace_bytes(tokens: int, dim: int, hidden: int) -> int:
 def swin_block(desc: AbSwinBlock) -> None:
     """One whole Swin3DTransformerBlock in place on the token stream (see include/aurora_b200.h)."""
     check(lib().ab_swin_block(C.byref(desc), _s()), "ab_swin_block")
+
+
+# ---- projection with adaLN + residual in the epilogue (csrc/gemm_ln.cu) -------------------------------------------
+class AbGemmLn(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+        ("residual", C.c_void_p), ("out_f32", C.c_void_p), ("out_16", C.c_void_p),
+        ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32),
+        ("lda", C.c_int32), ("ldw", C.c_int32), ("ldr", C.c_int32), ("ld_f32", C.c_int32), ("ld_16", C.c_int32),
+        ("in_dtype", C.c_int32), ("out_dtype", C.c_int32), ("eps", C.c_float),
+    ]
+
+
+def gemm_ln_supported(n: int) -> bool:
+    return bool(lib().ab_gemm_ln_supported(int(n)))
+
+
+def gemm_ln_residual(a: torch.Tensor, w: torch.Tensor, *, bias=None, scale=None, shift=None, residual=None, out_f32=None,
+                     out_bf16=None, eps: float = 1e-5) -> None:
+    """``out = residual + LN(a @ w.T + bias) * scale + shift`` in one kernel (N = 512 or 1024)."""
+    assert a.dtype == w.dtype
+    m, k = a.shape
+    n, k2 = w.shape
+    assert k == k2
+    g = AbGemmLn()
+    g.a, g.w, g.bias, g.scale, g.shift = ptr(a), ptr(w), ptr(bias), ptr(scale), ptr(shift)
+    for t in (bias, scale, shift):
+        assert t is None or (t.dtype == torch.float32 and t.numel() == n and t.is_contiguous())
+    g.m, g.n, g.k, g.lda, g.ldw = m, n, k, _ld(a), _ld(w)
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.shape == (m, n)
+        g.residual, g.ldr = ptr(residual), _ld(residual)
+    if out_f32 is not None:
+        assert out_f32.dtype == torch.float32 and out_f32.shape == (m, n)
+        g.out_f32, g.ld_f32 = ptr(out_f32), _ld(out_f32)
+    g.in_dtype = _dt(a)
+    if out_bf16 is not None:
+        assert out_bf16.shape == (m, n)
+        g.out_16, g.ld_16, g.out_dtype = ptr(out_bf16), _ld(out_bf16), _dt(out_bf16)
+    g.eps = eps
+    nb = 2.0 * m * k + 2.0 * n * k + m * n * ((4.0 if residual is not None else 0.0) + (4.0 if out_f32 is not None else 0.0)
+                                              + (2.0 if out_bf16 is not None else 0.0))
+    with _Timed("gemm_ln", work=2.0 * m * n * k, nbytes=nb):
+        check(lib().ab_gemm_ln_residual(C.byref(g), _s()), "ab_gemm_ln_residual")

@@ -9,6 +9,8 @@
 //   h     = GELU_erf(x_b16 · Wfc1^T + b)
 //   y     = h · Wfc2^T + b
 //   x     = x + LN(y) * scale2 + shift2
+// With `fuse_ln` and D = 512 / 1024 each "projection, then x = x + LN(y) ..." pair is ONE kernel (csrc/gemm_ln.cu):
+// the adaLN + residual runs in the projection's epilogue and y never reaches HBM.
 //
 // It only sequences the kernels of this library on the caller's stream (8 - 10 launches); the caller (PyTorch) owns
 // every buffer, the workspace included (ab_swin_block_workspace_bytes).
@@ -93,20 +95,38 @@ extern "C" int ab_swin_block(const AbSwinBlock* b, void* stream) {
   }
   if ((rc = ab_window_attention(&a, stream)) != AB_OK) return rc;
 
+  // adaLN + residual fused into the epilogue of the projection / fc2 where a cluster can own whole rows (csrc/gemm_ln.cu)
+  const bool fuse = b->fuse_ln != 0 && ab_gemm_ln_supported(d) != 0;
+  AbGemmLn gl = {};
+  gl.in_dtype = AB_DT_BF16, gl.out_dtype = AB_DT_BF16, gl.eps = b->eps;
+  gl.m = m, gl.n = d, gl.ldr = d, gl.ld_f32 = d, gl.ld_16 = d;
+  gl.residual = b->x_f32, gl.out_f32 = b->x_f32, gl.out_16 = b->x_b16;
+
   // output projection + adaLN 1 + residual
+  if (fuse) {
+    gl.a = att, gl.w = b->w_proj, gl.bias = b->b_proj, gl.scale = b->scale1, gl.shift = b->shift1;
+    gl.k = d, gl.lda = d, gl.ldw = d;
+    if ((rc = ab_gemm_ln_residual(&gl, stream)) != AB_OK) return rc;
+  }
   g.a = att, g.w = b->w_proj, g.bias = b->b_proj, g.out_bf16 = y;
   g.n = d, g.k = d, g.lda = d, g.ldw = d, g.ld_bf16 = d;
-  if ((rc = ab_gemm_bf16(&g, stream)) != AB_OK) return rc;
+  if (!fuse && (rc = ab_gemm_bf16(&g, stream)) != AB_OK) return rc;
   AbLnModResidual ln = {};
   ln.y = y, ln.scale = b->scale1, ln.shift = b->shift1, ln.residual = b->x_f32, ln.out_f32 = b->x_f32, ln.out_bf16 = b->x_b16;
   ln.rows = m, ln.dim = d, ln.ld_y = d, ln.ld_res = d, ln.ld_f32 = d, ln.ld_bf16 = d, ln.eps = b->eps;
   ln.in_dtype = AB_DT_BF16, ln.out_dtype = AB_DT_BF16;
-  if ((rc = ab_ln_mod_residual(&ln, stream)) != AB_OK) return rc;
+  if (!fuse && (rc = ab_ln_mod_residual(&ln, stream)) != AB_OK) return rc;
 
   // MLP + adaLN 2 + residual
   g.a = b->x_b16, g.w = b->w_fc1, g.bias = b->b_fc1, g.out_bf16 = hid, g.act = AB_ACT_GELU_ERF;
   g.n = b->hidden, g.k = d, g.lda = d, g.ldw = d, g.ld_bf16 = b->hidden;
   if ((rc = ab_gemm_bf16(&g, stream)) != AB_OK) return rc;
+  if (fuse) {
+    gl.a = hid, gl.w = b->w_fc2, gl.bias = b->b_fc2, gl.scale = b->scale2, gl.shift = b->shift2;
+    gl.k = b->hidden, gl.lda = b->hidden, gl.ldw = b->hidden;
+    if (b->out_b16 != nullptr) gl.out_16 = b->out_b16, gl.ld_16 = b->ld_out_b16, gl.out_dtype = b->out_b16_dtype;
+    return ab_gemm_ln_residual(&gl, stream);
+  }
   g.a = hid, g.w = b->w_fc2, g.bias = b->b_fc2, g.out_bf16 = y, g.act = AB_ACT_NONE;
   g.n = d, g.k = b->hidden, g.lda = b->hidden, g.ldw = b->hidden, g.ld_bf16 = d;
   if ((rc = ab_gemm_bf16(&g, stream)) != AB_OK) return rc;

@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import ctypes
 import dataclasses
+import os
 from datetime import timedelta
 from typing import Optional
 
@@ -106,6 +107,8 @@ class AuroraEngine:
         self._peer: Optional["sharding.PeerHalo"] = None
         self._slab_cache: dict = {}
         self.block_entry = True  # run Swin blocks through the whole-block entry point ab_swin_block
+        # adaLN + residual fused into the epilogue of proj / fc2 (ab_gemm_ln_residual) at the widths it supports
+        self.fuse_ln = os.environ.get("AB_FUSE_LN", "1") != "0"
         self._shard_plans = None
         # stage-level taps for parity tests: when set to a dict, `_run` stores fp32 copies of the encoder output and
         # of the residual stream after every Swin block / patch merge / patch split under the reference's module names
@@ -565,15 +568,25 @@ class AuroraEngine:
                 self._exchange(qkv4, halo, col_from=d)
             cabi.window_attention(qkv, att, batch=1, res=(c_, h_global, w_), window=ws, shift=ss, num_heads=heads,
                                   pad_qkv=pad, slab=(h_begin, rows_), halo_kv=halo)
-        cabi.gemm(att, wproj, bias=self._f32(f"{prefix}.attn.proj.bias"), out_bf16=y)
+        fuse = self.fuse_ln and cabi.gemm_ln_supported(d)  # adaLN + residual in the projection's epilogue (gemm_ln.cu)
         sc1, sh1 = self._modulation(f"{prefix}.norm1", d)
-        cabi.ln_mod_residual(y, scale=sc1, shift=sh1, residual=x_f32, out_f32=x_f32, out_bf16=x_b16)
+        if fuse:
+            cabi.gemm_ln_residual(att, wproj, bias=self._f32(f"{prefix}.attn.proj.bias"), scale=sc1, shift=sh1,
+                                  residual=x_f32, out_f32=x_f32, out_bf16=x_b16)
+        else:
+            cabi.gemm(att, wproj, bias=self._f32(f"{prefix}.attn.proj.bias"), out_bf16=y)
+            cabi.ln_mod_residual(y, scale=sc1, shift=sh1, residual=x_f32, out_f32=x_f32, out_bf16=x_b16)
         cabi.gemm(x_b16, self._bf16(f"{prefix}.mlp.fc1.weight"), bias=self._f32(f"{prefix}.mlp.fc1.bias"),
                   out_bf16=hid, act=GELU)
-        cabi.gemm(hid, self._bf16(f"{prefix}.mlp.fc2.weight"), bias=self._f32(f"{prefix}.mlp.fc2.bias"), out_bf16=y)
         sc2, sh2 = self._modulation(f"{prefix}.norm2", d)
-        cabi.ln_mod_residual(y, scale=sc2, shift=sh2, residual=x_f32, out_f32=x_f32,
-                             out_bf16=x_b16 if out_b16 is None else out_b16)
+        if fuse:
+            cabi.gemm_ln_residual(hid, self._bf16(f"{prefix}.mlp.fc2.weight"), bias=self._f32(f"{prefix}.mlp.fc2.bias"),
+                                  scale=sc2, shift=sh2, residual=x_f32, out_f32=x_f32,
+                                  out_bf16=x_b16 if out_b16 is None else out_b16)
+        else:
+            cabi.gemm(hid, self._bf16(f"{prefix}.mlp.fc2.weight"), bias=self._f32(f"{prefix}.mlp.fc2.bias"), out_bf16=y)
+            cabi.ln_mod_residual(y, scale=sc2, shift=sh2, residual=x_f32, out_f32=x_f32,
+                                 out_bf16=x_b16 if out_b16 is None else out_b16)
 
     def _slab_info(self, plan, i: int):
         """Band geometry of stage `i` and what this rank's NEIGHBOURS need from it: `to_above[shifted]` = how many of
@@ -619,6 +632,7 @@ class AuroraEngine:
         nbytes = cabi.swin_block_workspace_bytes(l, d, hidden)
         b.workspace = self._buffer("bb.ws", (nbytes,), torch.uint8).data_ptr()
         b.dim, b.hidden, b.num_heads, b.eps = d, hidden, heads, 1e-5
+        b.fuse_ln = int(self.fuse_ln)
         b.window, b.shift = cabi._i3(ws), cabi._i3(ss)
         keep = None
         if slab is None:

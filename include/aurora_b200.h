@@ -255,10 +255,40 @@ typedef struct AbSwinBlock {
   int32_t ld_out_b16, out_b16_dtype;
   int32_t slab_h_begin, slab_h_rows, halo_rows;
   float eps;
+  int32_t fuse_ln;  /* != 0: adaLN + residual in the epilogue of proj / fc2 (ab_gemm_ln_residual) where dim allows */
 } AbSwinBlock;
 
 int ab_swin_block_workspace_bytes(int64_t tokens, int32_t dim, int32_t hidden, size_t* bytes);
 int ab_swin_block(const AbSwinBlock* b, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Projection with AdaptiveLayerNorm + residual fused into its epilogue (swin3d.py:507-508 with film.py:48-49):
+ *
+ *   out[m, :] = residual[m, :] + LN( A[m, :] · W^T + bias ) * scale + shift
+ *
+ * = ab_gemm_bf16 followed by ab_ln_mod_residual, in one kernel: the projection output never goes to HBM (the
+ * statistics are taken on the fp32 accumulator in TMEM).  A cluster of CTA pairs owns whole rows, so N is fixed
+ * to 512 or 1024 (ab_gemm_ln_supported).  A, W: bf16|fp16 [M, K] / [N, K]; bias, scale, shift: f32 [N] or NULL
+ * (0 / 1 / 0); residual f32 [M, ldr] or NULL; outputs f32 [M, ld_f32] (may alias residual) and / or 16-bit
+ * [M, ld_16].  LN without affine, biased variance, eps as given.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct AbGemmLn {
+  const void* a;
+  const void* w;
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  const float* residual;
+  float* out_f32;
+  void* out_16;
+  int32_t m, n, k;
+  int32_t lda, ldw, ldr, ld_f32, ld_16;
+  int32_t in_dtype, out_dtype; /* AB_DT_* */
+  float eps;
+} AbGemmLn;
+
+int ab_gemm_ln_supported(int32_t n);
+int ab_gemm_ln_residual(const AbGemmLn* p, void* stream);
 
 /* PatchMerging3D front half (swin3d.py:526-553): x f32 [batch, C, H, W, D] -> zero pad H, W to even at
  * the bottom / right -> 2x2 gather with feature order (h w D) -> LayerNorm(4D) with affine gamma/beta

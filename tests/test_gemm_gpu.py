@@ -129,3 +129,66 @@ def test_gemm_rejects_bad_arguments():
     out = torch.zeros(16, 16, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(cabi.AbError):
         cabi.gemm(a, w, out_bf16=out)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# projection with adaLN + residual fused into the epilogue (csrc/gemm_ln.cu)
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,n,k", [
+    (1000, 512, 512),     # proj-like, M tail inside the second CTA of the pair
+    (5000, 512, 2048),    # fc2-like, many tiles per cluster, long K
+    (37, 512, 128),       # fewer rows than one CTA holds
+    (785, 1024, 1024),    # two CTA pairs per cluster: row statistics meet through distributed shared memory
+    (20000, 1024, 4096),  # stage-2 fc2-like
+    (300, 1024, 72),      # K tail (K % 64 != 0), P = 2
+])
+@pytest.mark.parametrize("mode", ["inplace_bf16", "f16_wide_ld", "no_residual_f32_only"])
+def test_gemm_ln_residual_matches_fp32_reference(m, n, k, mode):
+    """out = residual + LN(a @ w.T + bias) * scale + shift against plain fp32 PyTorch on the same 16-bit operands.
+    Tolerance: the kernel takes the statistics on the fp32 accumulator, so only summation order differs: 2e-3 abs / rel
+    on the fp32 stream (values are O(1..10)), one 16-bit ulp on the 16-bit copy."""
+    from aurora_b200 import cabi
+
+    torch.manual_seed(m + n + k)
+    dev = "cuda"
+    dt = torch.float16 if mode == "f16_wide_ld" else torch.bfloat16
+    a = torch.randn(m, k, device=dev).to(dt)
+    w = (torch.randn(n, k, device=dev) / k**0.5).to(dt)
+    bias = torch.randn(n, device=dev)
+    scale = torch.randn(n, device=dev)
+    shift = torch.randn(n, device=dev)
+    residual = None if mode == "no_residual_f32_only" else torch.randn(m, n, device=dev) * 3
+    y = a.float() @ w.float().t() + bias
+    ref = torch.nn.functional.layer_norm(y, (n,), eps=1e-5) * scale + shift
+    if residual is not None:
+        ref = ref + residual
+    if mode == "inplace_bf16":
+        out_f32 = residual.clone()              # the fp32 stream is updated IN PLACE (output aliases the residual)
+        out16 = torch.full((m, n), float("nan"), device=dev, dtype=dt)
+        cabi.gemm_ln_residual(a, w, bias=bias, scale=scale, shift=shift, residual=out_f32, out_f32=out_f32, out_bf16=out16)
+    elif mode == "f16_wide_ld":
+        wide = torch.full((m, 2 * n), float("nan"), device=dev, dtype=dt)   # one half of a concatenation buffer
+        out16 = wide[:, n:]
+        out_f32 = torch.full((m, n), float("nan"), device=dev)
+        cabi.gemm_ln_residual(a, w, bias=bias, scale=scale, shift=shift, residual=residual, out_f32=out_f32, out_bf16=out16)
+        assert torch.isnan(wide[:, :n]).all()   # the other half is untouched
+    else:
+        out16 = None
+        out_f32 = torch.full((m, n), float("nan"), device=dev)
+        cabi.gemm_ln_residual(a, w, bias=bias, scale=scale, shift=shift, out_f32=out_f32)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out_f32, ref, rtol=2e-3, atol=2e-3)
+    if out16 is not None:
+        torch.testing.assert_close(out16.float(), ref, rtol=1e-2, atol=2e-2)
+        assert torch.equal(out16, out_f32.to(dt))  # the 16-bit copy is the rounding of the fp32 result
+
+
+def test_gemm_ln_residual_rejects_other_widths():
+    from aurora_b200 import cabi
+
+    a = torch.zeros(256, 64, device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros(2048, 64, device="cuda", dtype=torch.bfloat16)
+    out = torch.zeros(256, 2048, device="cuda")
+    assert not cabi.gemm_ln_supported(2048) and cabi.gemm_ln_supported(512) and cabi.gemm_ln_supported(1024)
+    with pytest.raises(cabi.AbError, match="not supported"):
+        cabi.gemm_ln_residual(a, w, out_f32=out)
