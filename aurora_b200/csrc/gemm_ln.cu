@@ -11,11 +11,18 @@
 //   * every pair runs the cta_group::2 pipeline of gemm.cu on ITS 512 columns: M = 256 rows per cluster tile (128 per
 //     CTA), two accumulators of 256 fp32 columns = all 512 TMEM columns of both SMs (no accumulator double buffering:
 //     the epilogue is HBM-bound, the next tile's operands are prefetched under it);
-//   * epilogue, one thread per row and accumulator half (warp w: TMEM lane quadrant w & 3, half (w - 4) >> 2):
-//       pass A  sum(y)            -> mean      (partials meet in shared memory; P = 2: + one DSMEM exchange)
-//       pass B  sum((y - mean)^2) -> rstd      (two-pass variance, as the row kernel it replaces)
-//       pass C  residual + (y - mean) * rstd * scale + shift -> fp32 stream (may alias the residual) + 16-bit copy
-//     three reads of the accumulator out of TMEM (16 TB/s aggregate) instead of one trip through HBM.
+//   * epilogue, 16 warps, one thread per row and 128-column group (warp w: TMEM lane quadrant w & 3, group (w - 4) >> 2);
+//     an otherwise idle warp prefetches the NEXT tile's residual rows into L2 (cp.async.bulk.prefetch) under the
+//     current tile's main loop, so the epilogue's reads are L2 hits:
+//       pass 1  sum(y), sum(y^2) -> mean, rstd   (partials of the four warps that share a row meet in shared memory;
+//                                                 P = 2: + one DSMEM exchange with the CTA holding the other columns)
+//       pass 2  residual + (y - mean) * rstd * scale + shift -> fp32 stream (may alias the residual) + 16-bit copy
+//     two reads of the accumulator out of TMEM (16 TB/s aggregate) instead of one trip through HBM.  Pass 2 turns
+//     the "thread = row" TMEM layout into coalesced global accesses through a 2 KB per-warp shared-memory tile
+//     (32 rows x 16 columns, XOR-swizzled, conflict-free both ways): four lanes read one row's 64 bytes of the
+//     residual, add, and write 64 bytes of the fp32 stream / 32 bytes of the 16-bit copy.  (First version: every
+//     thread streamed its own row with 16-byte accesses — 32 cache lines per warp instruction — and reached 1.2 - 2.9
+//     TB/s; profiles/r02_kernel_probes.md.)
 //   * P = 2 (D = 1024): CTA r exchanges its per-row partial sums with CTA r ^ 2 (same rows, other 512 columns) through
 //     distributed shared memory: remote store + remote mbarrier arrive (release.cluster) / acquire.cluster wait.
 #include "common.h"
@@ -30,17 +37,20 @@ constexpr int kUmmaK = 16;
 constexpr int kHalfN = 256;          // one accumulator / one MMA N
 constexpr int kPairN = 2 * kHalfN;   // columns per CTA pair
 constexpr int kLoadN = 128;          // W rows staged per CTA and accumulator half
-constexpr int kNumEpiWarps = 8;
+constexpr int kNumEpiWarps = 16;     // four per TMEM lane quadrant: 128 of the pair's 512 columns each
+constexpr int kColsPerWarp = kPairN / 4;
 constexpr int kThreads = 128 + kNumEpiWarps * 32;
 constexpr int kStageBytesA = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kSubB = kLoadN * kBlockK * 2;          // 16 KB
 constexpr int kStageBytes = kStageBytesA + 2 * kSubB;  // 48 KB
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kOffVec = kStages * kStageBytes;         // bias | scale | shift of this pair's 512 columns (f32)
 constexpr int kVecBytes = 3 * kPairN * 4;
-constexpr int kOffStat = kOffVec + kVecBytes;          // partA[2][128] partB[2][128] remA[128] remB[128] bias_sum[2]
-constexpr int kStatBytes = (4 * 128 + 2 * 128 + 8) * 4;
-constexpr int kOffBar = kOffStat + kStatBytes;
+constexpr int kOffStat = kOffVec + kVecBytes;          // part[4][128] float2 (sum, sum of squares), rem[128] float2
+constexpr int kStatBytes = (4 * 128 * 2 + 128 * 2) * 4;
+constexpr int kOffStage = (kOffStat + kStatBytes + 127) & ~127;  // per epilogue warp: 32 rows x 16 fp32 columns
+constexpr int kStageOutBytes = 32 * 16 * 4;                     // 2 KB
+constexpr int kOffBar = kOffStage + kNumEpiWarps * kStageOutBytes;
 constexpr int kBarrierBytes = 256;
 constexpr int kSmemBytes = kOffBar + kBarrierBytes + 1024;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory");
@@ -122,18 +132,15 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   float* s_bias = reinterpret_cast<float*>(smem + kOffVec);
   float* s_scale = s_bias + kPairN;
   float* s_shift = s_scale + kPairN;
-  float* part_a = reinterpret_cast<float*>(smem + kOffStat);  // [2][128]
-  float* part_b = part_a + 256;                               // [2][128]
-  float* rem_a = part_b + 256;                                // [128]  partner CTA's row sums (P = 2)
-  float* rem_b = rem_a + 128;
-  float* bias_sum = rem_b + 128;                              // [2]
+  float2* part = reinterpret_cast<float2*>(smem + kOffStat);  // [4][128]: (sum, sum of squares) per column group and row
+  float2* rem = part + 4 * 128;                               // [128]: the partner CTA's row totals (P = 2)
+  uint8_t* stage_out = smem + kOffStage;                      // 8 x 2 KB transpose tiles
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 1;  // leader's
-  uint64_t* stat_a_bar = tmem_empty_bar + 1;     // P = 2: the partner CTA's four half-0 warps arrive here
-  uint64_t* stat_b_bar = stat_a_bar + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stat_b_bar + 1);
+  uint64_t* stat_bar = tmem_empty_bar + 1;       // P = 2: the partner CTA's four group-0 warps arrive here
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stat_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -155,8 +162,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     mbar_init(tmem_full_bar, 1);
     mbar_init(tmem_empty_bar, 2 * kNumEpiWarps);
-    mbar_init(stat_a_bar, 4);
-    mbar_init(stat_b_bar, 4);
+    mbar_init(stat_bar, 4);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc_pair<512>(tmem_slot);
@@ -170,15 +176,6 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   cluster_sync_all();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  if (warp == 3) {  // sum of the bias over each accumulator half (pass A adds it once per row)
-    for (int h = 0; h < 2; ++h) {
-      float s = 0.f;
-      for (int i = lane; i < kHalfN; i += 32) s += s_bias[h * kHalfN + i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) bias_sum[h] = s;
-    }
-  }
   __syncthreads();
 
   const int num_tiles = (g.m + 2 * kBlockM - 1) / (2 * kBlockM);
@@ -231,132 +228,134 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       if (tc > 0) mbar_wait(tmem_empty_bar, (tc - 1) & 1u);  // last remote arrivals land before the CTA may exit
     }
+  } else if (warp == 3) {
+    // ===== residual prefetch into L2, one tile ahead of the epilogue =====
+    if (g.residual != nullptr) {
+      uint32_t tc = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tc) {
+        const int row0 = tile * (2 * kBlockM) + static_cast<int>(rank & 1u) * kBlockM;
+        for (int rr = lane; rr < kBlockM; rr += 32) {
+          const int row = row0 + rr;
+          if (row < g.m) {
+            const float* p = g.residual + static_cast<size_t>(row) * g.ldr + n_base;  // this pair's 2 KB of the row
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(kPairN * 4) : "memory");
+          }
+        }
+        mbar_wait(tmem_full_bar, tc & 1u);  // this tile's main loop is done: go and fetch the next tile's rows
+      }
+    }
   } else if (warp >= 4) {
-    // ===== epilogue: thread = (row, accumulator half) =====
+    // ===== epilogue: thread = (row, 128-column group) =====
     const int q = warp & 3;            // TMEM lane quadrant
-    const int ch = (warp - 4) >> 2;    // accumulator half: columns [ch * 256, +256) of this pair's 512
+    const int cg = (warp - 4) >> 2;    // column group: columns [cg * 128, +128) of this pair's 512
     const int r = q * 32 + lane;       // row inside this CTA's 128
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ch * kHalfN;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cg * kColsPerWarp;  // accumulators are adjacent
     const float inv_n = 1.f / static_cast<float>(g.n);
-    const float* sb = s_bias + ch * kHalfN;
-    const float* ssc = s_scale + ch * kHalfN;
-    const float* ssh = s_shift + ch * kHalfN;
+    const float* sb = s_bias + cg * kColsPerWarp;
+    const float* ssc = s_scale + cg * kColsPerWarp;
+    const float* ssh = s_shift + cg * kColsPerWarp;
+    const uint32_t stg = smem_u32(stage_out + (warp - 4) * kStageOutBytes);
+    const uint32_t st_row = stg + lane * 64;
+    const int sw_w = (lane >> 1) & 3;  // write side of the transpose tile: row = lane
+    const int rr = lane >> 2, jj = lane & 3;  // read side: 8 rows per instruction, 4 lanes (16 B each) per row
     uint32_t tc = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tc) {
-      const int row = tile * (2 * kBlockM) + static_cast<int>(rank & 1u) * kBlockM + r;
-      const bool live = row < g.m;
       mbar_wait(tmem_full_bar, tc & 1u);
       tc_fence_after_sync();
-      // ---- pass A: mean ----
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      // ---- pass 1: sum and sum of squares of y = acc + bias over this warp's 128 columns ----
+      float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < kHalfN; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          s0 += __uint_as_float(v[j]);
-          s1 += __uint_as_float(v[j + 1]);
-          s2 += __uint_as_float(v[j + 2]);
-          s3 += __uint_as_float(v[j + 3]);
-        }
-      }
-      part_a[ch * 128 + r] = (s0 + s1) + (s2 + s3) + bias_sum[ch];
-      named_bar_sync(1 + q, 64);  // the two warps that share these 32 rows
-      float total = part_a[r] + part_a[128 + r];
-      if constexpr (P > 1) {
-        if (ch == 0) {
-          st_remote_f32(&rem_a[r], rank ^ 2u, total);
-          __syncwarp();
-          if (lane == 0) mbar_arrive_remote_release(stat_a_bar, rank ^ 2u);
-        }
-        mbar_wait_acquire_cluster(stat_a_bar, tc & 1u);
-        total += rem_a[r];
-      }
-      const float mean = total * inv_n;
-      // ---- pass B: variance around the mean ----
-      s0 = s1 = s2 = s3 = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < kHalfN; c += 32) {
+      for (int c = 0; c < kColsPerWarp; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + c, v);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const float4 b4 = *reinterpret_cast<const float4*>(sb + c + j);
-          const float d0 = __uint_as_float(v[j]) + (b4.x - mean), d1 = __uint_as_float(v[j + 1]) + (b4.y - mean);
-          const float d2 = __uint_as_float(v[j + 2]) + (b4.z - mean), d3 = __uint_as_float(v[j + 3]) + (b4.w - mean);
-          s0 = fmaf(d0, d0, s0);
-          s1 = fmaf(d1, d1, s1);
-          s2 = fmaf(d2, d2, s2);
-          s3 = fmaf(d3, d3, s3);
+          const float y0 = __uint_as_float(v[j]) + b4.x, y1 = __uint_as_float(v[j + 1]) + b4.y;
+          const float y2 = __uint_as_float(v[j + 2]) + b4.z, y3 = __uint_as_float(v[j + 3]) + b4.w;
+          s0 += y0 + y2;
+          s1 += y1 + y3;
+          q0 = fmaf(y0, y0, fmaf(y2, y2, q0));
+          q1 = fmaf(y1, y1, fmaf(y3, y3, q1));
         }
       }
-      part_b[ch * 128 + r] = (s0 + s1) + (s2 + s3);
-      named_bar_sync(1 + q, 64);
-      total = part_b[r] + part_b[128 + r];
+      part[cg * 128 + r] = make_float2(s0 + s1, q0 + q1);
+      named_bar_sync(1 + q, 128);  // the four warps that share these 32 rows
+      float2 tot = part[r];
+#pragma unroll
+      for (int i = 1; i < 4; ++i) {
+        const float2 t = part[i * 128 + r];
+        tot.x += t.x, tot.y += t.y;
+      }
       if constexpr (P > 1) {
-        if (ch == 0) {
-          st_remote_f32(&rem_b[r], rank ^ 2u, total);
+        if (cg == 0) {
+          st_remote_f32(&rem[r].x, rank ^ 2u, tot.x);
+          st_remote_f32(&rem[r].y, rank ^ 2u, tot.y);
           __syncwarp();
-          if (lane == 0) mbar_arrive_remote_release(stat_b_bar, rank ^ 2u);
+          if (lane == 0) mbar_arrive_remote_release(stat_bar, rank ^ 2u);
         }
-        mbar_wait_acquire_cluster(stat_b_bar, tc & 1u);
-        total += rem_b[r];
+        mbar_wait_acquire_cluster(stat_bar, tc & 1u);
+        const float2 t = rem[r];
+        tot.x += t.x, tot.y += t.y;
       }
-      const float rstd = rsqrtf(total * inv_n + g.eps);
-      // ---- pass C: normalise, modulate, add the residual, store the fp32 stream and its 16-bit copy ----
-      const size_t col0 = static_cast<size_t>(n_base + ch * kHalfN);
-      const float* res_row = g.residual != nullptr ? g.residual + static_cast<size_t>(row) * g.ldr + col0 : nullptr;
-      float* o32 = g.out_f32 != nullptr ? g.out_f32 + static_cast<size_t>(row) * g.ld_f32 + col0 : nullptr;
-      uint16_t* o16 = g.out_16 != nullptr ? g.out_16 + static_cast<size_t>(row) * g.ld_16 + col0 : nullptr;
+      const float mean = tot.x * inv_n;
+      const float rstd = rsqrtf(fmaxf(tot.y * inv_n - mean * mean, 0.f) + g.eps);
+      // ---- pass 2: normalise + modulate (thread = row), transpose through shared memory, then coalesced:
+      //      fp32 stream = residual + value, 16-bit copy ----
+      {
+        const int row_warp0 = tile * (2 * kBlockM) + static_cast<int>(rank & 1u) * kBlockM + q * 32;  // first row of this warp
+        const size_t col0 = static_cast<size_t>(n_base + cg * kColsPerWarp);
 #pragma unroll 1
-      for (int c = 0; c < kHalfN; c += 32) {
-        float4 rr[8];
-        if (live && res_row != nullptr) {
+        for (int c = 0; c < kColsPerWarp; c += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(taddr + c, v);
+          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) rr[j] = *reinterpret_cast<const float4*>(res_row + c + 4 * j);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) rr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + c, v);
-        tmem_ld_wait();
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b4 = *reinterpret_cast<const float4*>(sb + c + 4 * j);
-          const float4 sc4 = *reinterpret_cast<const float4*>(ssc + c + 4 * j);
-          const float4 sh4 = *reinterpret_cast<const float4*>(ssh + c + 4 * j);
-          f[4 * j + 0] = rr[j].x + fmaf((__uint_as_float(v[4 * j + 0]) + (b4.x - mean)) * rstd, sc4.x, sh4.x);
-          f[4 * j + 1] = rr[j].y + fmaf((__uint_as_float(v[4 * j + 1]) + (b4.y - mean)) * rstd, sc4.y, sh4.y);
-          f[4 * j + 2] = rr[j].z + fmaf((__uint_as_float(v[4 * j + 2]) + (b4.z - mean)) * rstd, sc4.z, sh4.z);
-          f[4 * j + 3] = rr[j].w + fmaf((__uint_as_float(v[4 * j + 3]) + (b4.w - mean)) * rstd, sc4.w, sh4.w);
-        }
-        if (live) {
-          if (o32 != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(o32 + c + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          for (int j = 0; j < 4; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + c + 4 * j);
+            const float4 sc4 = *reinterpret_cast<const float4*>(ssc + c + 4 * j);
+            const float4 sh4 = *reinterpret_cast<const float4*>(ssh + c + 4 * j);
+            const float f0 = fmaf((__uint_as_float(v[4 * j + 0]) + (b4.x - mean)) * rstd, sc4.x, sh4.x);
+            const float f1 = fmaf((__uint_as_float(v[4 * j + 1]) + (b4.y - mean)) * rstd, sc4.y, sh4.y);
+            const float f2 = fmaf((__uint_as_float(v[4 * j + 2]) + (b4.z - mean)) * rstd, sc4.z, sh4.z);
+            const float f3 = fmaf((__uint_as_float(v[4 * j + 3]) + (b4.w - mean)) * rstd, sc4.w, sh4.w);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + ((j ^ sw_w) << 4)), "f"(f0), "f"(f1),
+                         "f"(f2), "f"(f3)
+                         : "memory");
           }
-          if (o16 != nullptr) {
+          __syncwarp();
+          float4 val[4], res[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 p;
-              if (g.out_half) {
-                p.x = pack_f16x2(f[8 * j + 0], f[8 * j + 1]);
-                p.y = pack_f16x2(f[8 * j + 2], f[8 * j + 3]);
-                p.z = pack_f16x2(f[8 * j + 4], f[8 * j + 5]);
-                p.w = pack_f16x2(f[8 * j + 6], f[8 * j + 7]);
-              } else {
-                p.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-                p.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-                p.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-                p.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+          for (int i = 0; i < 4; ++i) {  // all four residual loads in flight before the first use
+            const int lr = i * 8 + rr;
+            const int grow = row_warp0 + lr;
+            res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (grow < g.m && g.residual != nullptr)
+              res[i] = *reinterpret_cast<const float4*>(g.residual + static_cast<size_t>(grow) * g.ldr + col0 + c + 4 * jj);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int lr = i * 8 + rr;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(val[i].x), "=f"(val[i].y), "=f"(val[i].z), "=f"(val[i].w)
+                         : "r"(stg + lr * 64 + ((jj ^ ((lr >> 1) & 3)) << 4)));
+          }
+          __syncwarp();  // every lane has read the tile: the next chunk may overwrite it while the stores drain
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int grow = row_warp0 + i * 8 + rr;
+            if (grow < g.m) {
+              const size_t col = col0 + c + 4 * jj;
+              float4 o = val[i];
+              o.x += res[i].x, o.y += res[i].y, o.z += res[i].z, o.w += res[i].w;
+              if (g.out_f32 != nullptr) *reinterpret_cast<float4*>(g.out_f32 + static_cast<size_t>(grow) * g.ld_f32 + col) = o;
+              if (g.out_16 != nullptr) {
+                uint2 p;
+                if (g.out_half) p.x = pack_f16x2(o.x, o.y), p.y = pack_f16x2(o.z, o.w);
+                else p.x = pack_bf16x2(o.x, o.y), p.y = pack_bf16x2(o.z, o.w);
+                *reinterpret_cast<uint2*>(g.out_16 + static_cast<size_t>(grow) * g.ld_16 + col) = p;
               }
-              *reinterpret_cast<uint4*>(o16 + c + 8 * j) = p;
             }
           }
         }

@@ -107,8 +107,11 @@ class AuroraEngine:
         self._peer: Optional["sharding.PeerHalo"] = None
         self._slab_cache: dict = {}
         self.block_entry = True  # run Swin blocks through the whole-block entry point ab_swin_block
-        # adaLN + residual fused into the epilogue of proj / fc2 (ab_gemm_ln_residual) at the widths it supports
-        self.fuse_ln = os.environ.get("AB_FUSE_LN", "1") != "0"
+        # adaLN + residual fused into the epilogue of proj / fc2 (ab_gemm_ln_residual, D = 512 / 1024).  OFF by default:
+        # measured on B200 (profiles/r02_kernel_probes.md) the fused kernel is correct but 3 - 60 % SLOWER than the
+        # double-buffered GEMM followed by the row kernel, because a cluster that owns whole rows fills TMEM with one
+        # tile and cannot overlap its HBM-bound epilogue with the next main loop.  AB_FUSE_LN=1 turns it on.
+        self.fuse_ln = os.environ.get("AB_FUSE_LN", "0") == "1"
         self._shard_plans = None
         # stage-level taps for parity tests: when set to a dict, `_run` stores fp32 copies of the encoder output and
         # of the residual stream after every Swin block / patch merge / patch split under the reference's module names
