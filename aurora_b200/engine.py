@@ -615,7 +615,30 @@ class AuroraEngine:
 
     def _tap(self, name: str, t: torch.Tensor) -> None:
         if self.taps is not None:
-            self.taps[name] = t.float().clone()
+            self.taps.setdefault(name, []).append(t.float().clone())  # one entry per batch element
+
+    @torch.inference_mode()
+    def backbone_forward(self, x: torch.Tensor, lead_time, rollout_step: int, patch_res) -> torch.Tensor:
+        """`Swin3DTransformerBackbone.forward(x, lead_time, rollout_step, patch_res)` (swin3d.py:884-936) on the
+        engine's kernels: x (B, L, D) float32 on the device -> (B, L, 2 D) float32.  Called by the `model.backbone` seam."""
+        cfg = self.cfg
+        if lead_time != cfg.timestep:
+            raise NotImplementedError(
+                f"the time conditioning is cached for the model time step ({cfg.timestep}); got lead_time = {lead_time}")
+        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 3):
+            raise ValueError("backbone.forward expects a float32 CUDA tensor of shape (B, L, D)")
+        patch_res = tuple(int(v) for v in patch_res)
+        assert x.shape[1] == patch_res[0] * patch_res[1] * patch_res[2], "Input shape does not match patch size."
+        assert x.shape[2] == cfg.embed_dim
+        l, d0 = x.shape[1], cfg.embed_dim
+        x_f32 = self._buffer("x0", (l, d0), torch.float32)
+        x_b16 = self._buffer("xb0", (l, d0), torch.bfloat16)
+        out = torch.empty(x.shape[0], l, 2 * d0, dtype=torch.float32, device=self.device)
+        for b in range(x.shape[0]):
+            x_f32.copy_(x[b])
+            x_b16.copy_(x[b])
+            out[b].copy_(self._backbone(x_f32, x_b16, patch_res, int(rollout_step)))
+        return out
 
     def _block_entry(self, prefix, x_f32, x_b16, res, heads, ws, ss, shifted, wqkv, wproj, out_b16, slab) -> None:
         l, d = x_f32.shape

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import dataclasses
 import warnings
+import weakref
 from datetime import timedelta
 from typing import Optional
 
@@ -36,6 +37,33 @@ class _ParamNode(nn.Module):
                 node.add_module(part, _ParamNode())
             node = node._modules[part]
         node.register_parameter(path[-1], nn.Parameter(value, requires_grad=False))
+
+
+class _BackboneSeam(_ParamNode):
+    """`model.backbone`: the parameters of the reference's `Swin3DTransformerBackbone` under the same names, and its
+    `forward` signature (swin3d.py:884-890) routed into the engine.  `Aurora.forward` itself runs the fused path and does
+    not go through this method, but forward hooks registered here (and on `model.encoder`) are honoured: they are
+    called with the stage's output, as for the reference's modules."""
+
+    def forward(self, x: torch.Tensor, lead_time: timedelta, rollout_step: int, patch_res) -> torch.Tensor:
+        owner = self.__dict__["_owner"]()
+        if not owner.autocast:
+            raise NotImplementedError("aurora_b200 has no fp32-exact mode: construct the model with autocast=True")
+        return owner._get_engine().backbone_forward(x, lead_time, rollout_step, patch_res)
+
+
+class _EncoderSeam(_ParamNode):
+    """`model.encoder`: parameter container; forward hooks registered on it receive the encoder output (B, L, D) of
+    every `Aurora.forward` call.  Its own `forward` is not offered: the encoder is fused with `Batch.normalise` and the
+    variant hooks inside the patch loader (csrc/patch_io.cu), so there is no stand-alone "normalised Batch in" entry."""
+
+    def forward(self, *a, **k):
+        raise NotImplementedError(
+            "aurora_b200 fuses normalisation and the encoder's patch embedding; run model.forward(batch) and read the "
+            "encoder output with a forward hook on model.encoder")
+
+
+_SEAMS = {"backbone": _BackboneSeam, "encoder": _EncoderSeam}
 
 
 class Aurora(nn.Module):
@@ -123,7 +151,9 @@ class Aurora(nn.Module):
         self.__dict__.pop("_plist", None)
         path = key.split(".")
         if path[0] not in self._modules:
-            self.add_module(path[0], _ParamNode())
+            node = _SEAMS.get(path[0], _ParamNode)()
+            node.__dict__["_owner"] = weakref.ref(self)
+            self.add_module(path[0], node)
         self._modules[path[0]].put(path[1:], value)
 
     # -- forward ----------------------------------------------------------------------------------
@@ -169,7 +199,25 @@ class Aurora(nn.Module):
                 "`autocast=True` recipe) and has no fp32-exact mode: construct the model with `autocast=True` (or set "
                 "`model.autocast = True`) to run it.")
         batch = self.batch_transform_hook(batch)
-        return self._get_engine().forward(batch, sharded=sharded)
+        eng = self._get_engine()
+        hooked = [(nm, m) for nm, m in (("encoder", self._modules.get("encoder")), ("backbone", self._modules.get("backbone")))
+                  if m is not None and m._forward_hooks]
+        if not hooked:
+            return eng.forward(batch, sharded=sharded)
+        # forward hooks on the stage seams (the reference's parity tooling taps `model.encoder` / `model.backbone` this
+        # way): run with stage taps and hand every hook the stage OUTPUT, (B, L, D) / (B, L, 2 D) float32
+        saved, eng.taps = eng.taps, {}
+        graph, eng.use_cuda_graph = eng.use_cuda_graph, False
+        try:
+            pred = eng.forward(batch, sharded=sharded)
+            taps = eng.taps
+        finally:
+            eng.taps, eng.use_cuda_graph = saved, graph
+        for nm, mod in hooked:
+            out = torch.stack(taps[nm], 0)
+            for hook in list(mod._forward_hooks.values()):
+                hook(mod, (), out)
+        return pred
 
     def batch_transform_hook(self, batch: Batch) -> Batch:
         return batch

@@ -52,7 +52,7 @@ def run_ours(model, dev_batch, levels):
     model.forward(dev_batch)
     torch.cuda.synchronize()
     buf = {nm: t for (nm, _, _), t in eng._buf.items()}
-    return {"x": eng.taps["encoder"], "xs0": buf["enc.xs0"].float().clone(), "xa": buf["enc.xa"].float().clone(),
+    return {"x": eng.taps["encoder"][-1], "xs0": buf["enc.xs0"].float().clone(), "xa": buf["enc.xa"].float().clone(),
             "lat1": buf["enc.lat1"].float().clone(), "posscale": eng._grid_cache[2].clone(), "lead": eng.lead_emb.clone(),
             "abs": next(iter(eng._abs_cache.values())).clone(),
             "lev_enc": eng._level_cache[tuple(levels)]["enc"].clone(),

@@ -36,7 +36,7 @@ def main():
     eng.taps = {}
     model.forward(dev_batch)
     torch.cuda.synchronize()
-    ours = eng.taps
+    ours = {k: v[-1] for k, v in eng.taps.items()}
     eng.taps = None
     model._engine = None
     del model, eng

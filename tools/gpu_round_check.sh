@@ -32,6 +32,12 @@ refarm)
 probe)
   ( time timeout 300 python experimental/probe_attn_x1.py ) > gpurun_out/probe_attn_x1.log 2>&1; echo "probe rc=$?"
   tail -12 gpurun_out/probe_attn_x1.log | cut -c1-400 ;;
+graph)
+  ( time timeout 400 python bench.py --steps 10 --warmup 3 --cuda-graph --rollout 40 --no-cpu-baseline --no-gpu-reference ) > gpurun_out/bench_graph.json 2> gpurun_out/bench_graph.err; echo "graph rc=$?"
+  python tools/show_bench.py gpurun_out/bench_graph.json ;;
+ncufull)
+  ( time timeout 600 ncu --set full --clock-control none --import-source on -k regex:'window_attention_tc|gemm2_bf16|gemm_ln|ln_mod_residual' -c 8 -o gpurun_out/r02_prof python tools/ncu_targets.py ) > gpurun_out/ncu_full.log 2>&1; echo "ncufull rc=$?"
+  tail -3 gpurun_out/ncu_full.log | cut -c1-300; ls -la gpurun_out/r02_prof.ncu-rep ;;
 ncu)
   ( time timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
       -k regex:'gemm|window_attention|ln_mod|patch|perceiver|linear_small|halo' --csv --log-file gpurun_out/launches.csv \
