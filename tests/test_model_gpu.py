@@ -274,6 +274,7 @@ def test_whole_block_entry_point_equals_the_per_kernel_path():
     batch = fx.make_batch(cfg, 192, 256, levels=fx.LEVELS4, b=1, seed=29, rollout_step=1)
     eng = model._get_engine()
     assert eng.block_entry
+    model.forward(batch)   # packs weights and caches the location-independent vectors (one-time launches)
     n0 = cabi.launch_count()
     fused = model.forward(batch)
     n_fused = cabi.launch_count() - n0
