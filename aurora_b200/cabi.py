@@ -234,6 +234,7 @@ class AbWindowAttention(C.Structure):
         ("slab_halo", C.c_int32),
         ("reserved_", C.c_int32),
         ("halo_kv", C.c_void_p),
+        ("halo_ctrl", C.c_void_p),
     ]
 
 
@@ -338,7 +339,7 @@ def window_index_map_host(res, window, shift, warped: bool = True):
 def window_attention(qkv: torch.Tensor, out: torch.Tensor, *, batch: int, res, window, shift, num_heads: int,
                      pad_qkv: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
                      warped: bool = True, slab: Optional[tuple[int, int]] = None,
-                     halo_kv: Optional[torch.Tensor] = None) -> None:
+                     halo_kv: Optional[torch.Tensor] = None, halo_ctrl: Optional[int] = None) -> None:
     """`slab=(h_begin, h_rows)`: qkv / out hold only those rows of the global grid `res` (latitude sharding);
     `halo_kv` is bf16 [2, C, halo, W, 2D]: K | V of the rows above / below the slab (cyclic)."""
     assert qkv.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and qkv.is_contiguous() and out.is_contiguous()
@@ -364,6 +365,7 @@ def window_attention(qkv: torch.Tensor, out: torch.Tensor, *, batch: int, res, w
             assert halo_kv.shape[4] == 2 * d
             a.slab_halo = halo_kv.shape[2]
             a.halo_kv = ptr(halo_kv)
+            a.halo_ctrl = halo_ctrl  # peer transport: the kernel waits for the neighbours' pushes itself
     nw, nt, _ = window_geometry(res, window, shift)
     with _Timed("window_attention", work=4.0 * batch * nw * num_heads * nt * nt * 64, nbytes=8.0 * tokens * d):
         check(lib().ab_window_attention(C.byref(a), _s()), "ab_window_attention")

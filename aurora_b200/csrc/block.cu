@@ -88,7 +88,7 @@ extern "C" int ab_swin_block(const AbSwinBlock* b, void* stream) {
       AbHaloPush hp = *b->halo_push;
       hp.local = qkv;
       if ((rc = ab_halo_push(&hp, stream)) != AB_OK) return rc;
-      if ((rc = ab_halo_wait(hp.ctrl, stream)) != AB_OK) return rc;
+      a.halo_ctrl = hp.ctrl;  // the attention kernel waits for the neighbours' rows itself, interior windows first
     }
     a.slab_h_begin = b->slab_h_begin, a.slab_h_rows = b->slab_h_rows, a.slab_halo = b->halo_rows;
     a.halo_kv = b->halo_kv;

@@ -43,6 +43,10 @@ struct AttnArgs {
   // global (C, H, W) grid; `halo` rows above and below (cyclic in H) come from halo_kv [2][C][halo][W][2D] (K | V columns only).
   int slab, h_begin, h_rows, halo, kh_begin, kh_count;
   const __nv_bfloat16* halo_kv;
+  // Peer-memory halo transport (csrc/halo.cu): control words of this rank's halo buffer.  When set, the loaders wait
+  // (ld.acquire.sys) until both neighbours' pushes of the current round have landed before they touch a foreign row —
+  // and in any case before the kernel ends, which keeps neighbouring ranks at most one exchange apart.
+  const uint32_t* halo_ctrl;
 };
 
 __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc) {
@@ -420,10 +424,15 @@ __device__ __forceinline__ TcItem tc_decode(const AttnArgs& a, long long item) {
   item /= a.num_heads;
   const WinGeom& g = a.g;
   if (a.slab) {
+    // Window rows are the SLOWEST index and the band's first / last window row — the only ones that can hold a
+    // neighbour's rows — come last: every CTA works through interior windows first, so the neighbours' halo pushes land
+    // under that work and the loaders' wait for them (below) is normally over before it starts.
     it.k2 = static_cast<int>(item % g.nwin[2]);
     item /= g.nwin[2];
-    it.k1 = (a.kh_begin + static_cast<int>(item % a.kh_count)) % g.nwin[1];
-    it.k0 = static_cast<int>(item / a.kh_count);
+    it.k0 = static_cast<int>(item % g.nwin[0]);
+    const int j = static_cast<int>(item / g.nwin[0]);  // 0 .. kh_count - 1 in processing order
+    const int idx = a.kh_count <= 2 ? j : (j < a.kh_count - 2 ? j + 1 : (j == a.kh_count - 2 ? 0 : a.kh_count - 1));
+    it.k1 = (a.kh_begin + idx) % g.nwin[1];
     it.b = 0;
   } else {
     const int win = static_cast<int>(item % g.nwindows);
@@ -518,6 +527,28 @@ __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// Wait until both neighbours' halo pushes of the current round have landed (protocol: csrc/halo.cu).  ctrl[0] / ctrl[1]
+// are written by the ranks above / below with st.release.sys, ctrl[2] is this rank's own round (its push precedes this
+// kernel on the stream).  The rows then arrive through TMA (async proxy): fence the proxies after the acquire.
+__device__ __forceinline__ void halo_wait_flags(const uint32_t* ctrl, int lane) {
+  if (lane < 2) {
+    const uint32_t want = ctrl[2];
+    uint64_t t0 = 0;
+    for (uint32_t spin = 1;; ++spin) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ctrl + lane) : "memory");
+      if (static_cast<int32_t>(v - want) >= 0) break;
+      if ((spin & 0xFFFu) == 0) {
+        const uint64_t now = global_timer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 20000000000ull) __trap();  // 20 s: a neighbour died
+      }
+    }
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_halo,
                            const AttnArgs a) {
@@ -560,6 +591,11 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
 
   if (warp < 2) {
     // ===== loaders: warp w takes items n = w (mod 2); item n lives in ring stage n % kStages =====
+    bool halo_ok = a.halo_ctrl == nullptr;
+    if (!halo_ok && warp >= cnt) {  // a loader without work still holds the kernel until the neighbours' pushes landed
+      halo_wait_flags(a.halo_ctrl, lane);
+      halo_ok = true;
+    }
     for (int n = warp; n < cnt; n += 2) {
       const int st = n % kStages;
       uint8_t* stage = smem + st * kStageBytes;
@@ -585,6 +621,15 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
         meta->batch[st] = it.b;
       }
       __syncwarp();
+      if (!halo_ok) {
+        // does this item read a neighbour's row?  (or is it this loader's last item: then wait regardless)
+        int foreign = 0;
+        for (int t = lane; t < kTok; t += 32) foreign |= (meta->lsrc[st][t] >= 0 && (meta->lsrc[st][t] & kHaloFlag)) ? 1 : 0;
+        if (__any_sync(0xffffffffu, foreign) || n + 2 >= cnt) {
+          halo_wait_flags(a.halo_ctrl, lane);
+          halo_ok = true;
+        }
+      }
       const long long row_base = static_cast<long long>(it.b) * a.tokens_per_batch;
       if (a.box_rows > 0) {
         // TMA gather: every run of `box_rows` consecutive in-window tokens along W is either all padding or one
@@ -955,6 +1000,7 @@ extern "C" int ab_window_attention(const AbWindowAttention* p, void* stream) {
   a.kh_begin = 0;
   a.kh_count = a.g.nwin[1];
   a.halo_kv = reinterpret_cast<const __nv_bfloat16*>(p->halo_kv);
+  a.halo_ctrl = p->halo_ctrl;
   if (a.slab) {
     AB_CHECK_ARG(p->batch == 1, "ab_window_attention: a latitude slab needs batch == 1");
     AB_CHECK_ARG(a.g.ntok == tc::kTok && p->bias == nullptr,

@@ -564,13 +564,16 @@ class AuroraEngine:
             h_begin, h_global, to_above, to_below = slab
             c_, rows_, w_ = res
             qkv4 = qkv.view(c_, rows_, w_, 3 * d)
+            ctrl = None
             if self._peer is not None:
-                halo = self._peer.exchange(qkv4, sharding.HALO, to_above[shifted], to_below[shifted], col_from=d)
+                halo = self._peer.exchange(qkv4, sharding.HALO, to_above[shifted], to_below[shifted], col_from=d,
+                                           wait=False)
+                ctrl = self._peer.base  # the attention kernel waits for the neighbours' rows, interior windows first
             else:
                 halo = self._buffer("bb.halo", (2, c_, sharding.HALO, w_, 2 * d), torch.bfloat16)
                 self._exchange(qkv4, halo, col_from=d)
             cabi.window_attention(qkv, att, batch=1, res=(c_, h_global, w_), window=ws, shift=ss, num_heads=heads,
-                                  pad_qkv=pad, slab=(h_begin, rows_), halo_kv=halo)
+                                  pad_qkv=pad, slab=(h_begin, rows_), halo_kv=halo, halo_ctrl=ctrl)
         fuse = self.fuse_ln and cabi.gemm_ln_supported(d)  # adaLN + residual in the projection's epilogue (gemm_ln.cu)
         sc1, sh1 = self._modulation(f"{prefix}.norm1", d)
         if fuse:

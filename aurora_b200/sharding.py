@@ -195,12 +195,13 @@ class PeerHalo:
         self.index = 0
 
     def exchange(self, local: torch.Tensor, halo: int, rows_to_above: int, rows_to_below: int,
-                 col_from: int = 0) -> torch.Tensor:
+                 col_from: int = 0, wait: bool = True) -> torch.Tensor:
         """`local` = this rank's band `[C, rows, W, K]` (contiguous, 2-byte elements).  Sends columns `[col_from, K)`
         of its first `rows_to_above` rows to the rank above and of its last `rows_to_below` rows to the rank below
         (what THEIR windows reach into this band, `halo_needs`), and returns this rank's halo
         `[2, C, halo, W, K - col_from]`: index 0 = rows above the band (the nearest ones valid, at the END of the
-        `halo` rows), index 1 = rows below (nearest first); valid once the stream reaches this point."""
+        `halo` rows), index 1 = rows below (nearest first); valid once the stream reaches this point (`wait=True`) or
+        once the consumer has waited on the control words itself (`wait=False`)."""
         cabi = self._cabi
         c, rows, w, k = local.shape
         kk = k - col_from
@@ -213,7 +214,8 @@ class PeerHalo:
         cabi.halo_push(local, above_slot=self.above + region + side, below_slot=self.below + region,
                        above_flag=self.above + 4, below_flag=self.below, ctrl=self.base, slot_rows=halo,
                        rows_to_above=rows_to_above, rows_to_below=rows_to_below, col_from=col_from)
-        cabi.halo_wait(self.base)
+        if wait:  # `wait=False`: the consumer (the attention kernel, given `self.base` as halo_ctrl) waits itself
+            cabi.halo_wait(self.base)
         return self.buf[region:region + 2 * side].view(local.dtype).view(2, c, halo, w, kk)
 
     def descriptor(self, shape: tuple, dtype: torch.dtype, halo: int, rows_to_above: int, rows_to_below: int,

@@ -392,16 +392,30 @@ def gemm_traffic(workload: str, launches: int, algo_bytes: float) -> dict:
 
 
 # ------------------------------------------------------------------------------------------------
-def resolve_parallelism(gpus: int, mode: str) -> str:
+def resolve_parallelism(workload: str, gpus: int, mode: str) -> str:
+    """`auto`: one forecast latitude-sharded over the GPUs whenever the workload's token grid can be split (bands must be
+    multiples of 4 token rows so that the U-Net's 2x2 patch merges stay inside a band); otherwise independent replicas."""
     if gpus <= 1:
         return "single GPU"
-    return "replicas" if mode == "replicas" else "latshard"
+    if mode == "replicas":
+        return "replicas"
+    from aurora_b200 import sharding
+
+    cfg = _our_config(workload)
+    _, h, _, _ = WORKLOADS[workload]
+    try:
+        sharding.plan_slabs((h - h % cfg.patch_size) // cfg.patch_size, len(cfg.encoder_depths), gpus)
+    except (NotImplementedError, ValueError):
+        if mode == "latshard":
+            raise
+        return "replicas"
+    return "latshard"
 
 
 def workload_config(workload: str, gpus: int = 1, mode: str = "auto") -> dict:
     """`config`: identical in both arms for the same command line (the driver compares it between the arms)."""
     cls, h, w, levels = WORKLOADS[workload]
-    par = resolve_parallelism(gpus, mode)
+    par = resolve_parallelism(workload, gpus, mode)
     return {"workload": workload, "model_class": cls, "grid": f"{h}x{w}", "levels": len(levels), "batch": 1,
             "history": 2, "algorithmic_tflop_per_step": ALGO_TFLOP[workload],
             "parallelism": {"single GPU": "single GPU", "replicas": f"replicas x{gpus} (one forecast per GPU)",
@@ -490,7 +504,7 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    latshard = distributed and args.parallelism in ("auto", "latshard")
+    latshard = distributed and resolve_parallelism(args.workload, world, args.parallelism) == "latshard"
     if args.cuda_graph is None:
         args.cuda_graph = latshard
     model.use_cuda_graph = bool(args.cuda_graph)

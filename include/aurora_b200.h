@@ -120,6 +120,10 @@ typedef struct AbWindowAttention {
   int32_t slab_h_begin, slab_h_rows, slab_halo;
   int32_t reserved_;
   const void* halo_kv;
+  /* Peer-memory transport: control words of this rank's halo buffer (AbHaloPush.ctrl) or NULL.  When given, the kernel
+   * itself waits for both neighbours' pushes of the current round — just before its first foreign row, interior windows
+   * run first — and ab_halo_wait must NOT be enqueued separately.  NULL: halo_kv is complete when the kernel starts. */
+  const uint32_t* halo_ctrl;
 } AbWindowAttention;
 
 int ab_window_attention(const AbWindowAttention* p, void* stream);
@@ -178,7 +182,9 @@ typedef struct AbHaloPush {
 
 /* Copy the first / last rows of every level of `local` into the neighbours' slots and publish the round. */
 int ab_halo_push(const AbHaloPush* p, void* stream);
-/* Block the stream until BOTH neighbours' pushes of the current round have landed in this rank's slots. */
+/* Block the stream until BOTH neighbours' pushes of the current round have landed in this rank's slots.  (The window
+ * attention kernel does this itself when it is given AbWindowAttention.halo_ctrl; this stand-alone wait serves other
+ * consumers and tests.) */
 int ab_halo_wait(uint32_t* ctrl, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
