@@ -50,6 +50,7 @@ class AbGemm(C.Structure):
         ("act", C.c_int32),
         ("in_dtype", C.c_int32),
         ("out_dtype", C.c_int32),
+        ("peer_push", C.c_void_p),
     ]
 
 
@@ -544,7 +545,7 @@ class AbSwinBlock(C.Structure):
         ("res", C.c_int32 * 3), ("window", C.c_int32 * 3), ("shift", C.c_int32 * 3),
         ("ld_out_b16", C.c_int32), ("out_b16_dtype", C.c_int32),
         ("slab_h_begin", C.c_int32), ("slab_h_rows", C.c_int32), ("halo_rows", C.c_int32),
-        ("eps", C.c_float), ("fuse_ln", C.c_int32),
+        ("eps", C.c_float), ("fuse_ln", C.c_int32), ("fuse_push", C.c_int32),
     ]
 
 

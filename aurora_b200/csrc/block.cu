@@ -77,18 +77,26 @@ extern "C" int ab_swin_block(const AbSwinBlock* b, void* stream) {
   // qkv projection
   g.a = b->x_b16, g.w = b->w_qkv, g.bias = b->b_qkv, g.out_bf16 = qkv;
   g.n = 3 * d, g.k = d, g.lda = d, g.ldw = d, g.ld_bf16 = 3 * d;
+  // fused compute + exchange: the projection's epilogue stores the boundary K | V rows into the neighbours' memory
+  const bool slab_push = b->slab_h_rows > 0 && b->halo_push != nullptr;
+  const bool fused_push = slab_push && b->fuse_push != 0 && (b->halo_push->rows_to_above + b->halo_push->rows_to_below) > 0 &&
+                          2 * b->halo_push->c <= 8;
+  if (fused_push) g.peer_push = b->halo_push;
   if ((rc = ab_gemm_bf16(&g, stream)) != AB_OK) return rc;
+  g.peer_push = nullptr;
 
   AbWindowAttention a = {};
   a.qkv = qkv, a.pad_qkv = b->pad_qkv, a.out = att;
   a.batch = 1, a.num_heads = b->num_heads, a.head_dim = 64, a.warped = 1;
   for (int i = 0; i < 3; ++i) a.res[i] = b->res[i], a.window[i] = b->window[i], a.shift[i] = b->shift[i];
   if (slab) {
-    if (b->halo_push != nullptr) {  // peer transport: push my boundary K | V rows, wait for the neighbours'
-      AbHaloPush hp = *b->halo_push;
-      hp.local = qkv;
-      if ((rc = ab_halo_push(&hp, stream)) != AB_OK) return rc;
-      a.halo_ctrl = hp.ctrl;  // the attention kernel waits for the neighbours' rows itself, interior windows first
+    if (b->halo_push != nullptr) {  // peer transport: my boundary K | V rows go to the neighbours ...
+      if (!fused_push) {            // ... by the copy kernel, unless the projection above has already sent them
+        AbHaloPush hp = *b->halo_push;
+        hp.local = qkv;
+        if ((rc = ab_halo_push(&hp, stream)) != AB_OK) return rc;
+      }
+      a.halo_ctrl = b->halo_push->ctrl;  // the attention kernel waits for the neighbours' rows itself, interior windows first
     }
     a.slab_h_begin = b->slab_h_begin, a.slab_h_rows = b->slab_h_rows, a.slab_halo = b->halo_rows;
     a.halo_kv = b->halo_kv;

@@ -13,6 +13,7 @@
 //
 // Replaces: every nn.Linear on Aurora's forward path (see include/aurora_b200.h).
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -39,6 +40,20 @@ struct GemmCfg {
   static_assert((2 * kStages + 4) * 8 + 4 <= kBarrierBytes, "barrier area");
 };
 
+// Rows of the 16-bit output that are ALSO stored into a neighbouring GPU's memory by the epilogue (the K | V halo rows of
+// a latitude-sharded forecast: the QKV projection pushes them over NVLink itself, fused compute + exchange, instead of
+// a separate copy kernel; protocol and buffer layout: csrc/halo.cu).  Up to 8 row ranges = 2 sides x 4 levels.
+struct PeerRows {
+  int n_ranges;         // 0 = off
+  int col_from;         // only boxes whose first column is >= col_from are sent (multiple of 64)
+  int dst_ld;           // destination row pitch in elements
+  int expected;         // number of 32-row x 64-column epilogue boxes of this launch that carry peer rows
+  int row_begin[8], row_end[8];
+  uint16_t* dst[8];     // peer address of (row_begin[i], col_from)
+  uint32_t* flag[2];    // the neighbours' "rows landed" flags
+  uint32_t* ctrl;       // this rank's control words: [2] round, [3] completion counter
+};
+
 struct GemmArgs {
   const float* bias;
   const float* residual;
@@ -50,7 +65,38 @@ struct GemmArgs {
   int vec_ok;    // all leading dimensions / pointers allow 16-byte vector access
   int out_half;  // 16-bit output is fp16 instead of bf16
   int tma_out;   // 16-bit-only output written through swizzled smem + TMA store (tmap_out valid)
+  PeerRows peer;
 };
+
+// This lane's destination in a neighbour's memory for the box (rows row0 + lane, columns col .. col + 64), or nullptr.
+__device__ __forceinline__ uint16_t* peer_row_ptr(const GemmArgs& g, int row, int col) {
+  uint16_t* p = nullptr;
+  if (g.peer.n_ranges > 0 && col >= g.peer.col_from && row < g.m) {
+#pragma unroll 1
+    for (int i = 0; i < g.peer.n_ranges; ++i)
+      if (row >= g.peer.row_begin[i] && row < g.peer.row_end[i])
+        p = g.peer.dst[i] + static_cast<size_t>(row - g.peer.row_begin[i]) * g.peer.dst_ld + (col - g.peer.col_from);
+  }
+  return p;
+}
+
+// After a box with peer rows: make the stores visible system-wide, count the box, and let the LAST box of the launch
+// publish the new round in both neighbours' flags (same hand-over as halo_push_kernel).
+__device__ __forceinline__ void peer_box_done(const GemmArgs& g, int lane) {
+  __threadfence_system();
+  __syncwarp();
+  if (lane == 0) {
+    const unsigned done = atomicAdd(&g.peer.ctrl[3], 1u);
+    if (done == static_cast<unsigned>(g.peer.expected) - 1u) {
+      __threadfence_system();
+      const uint32_t round = g.peer.ctrl[2] + 1u;
+      g.peer.ctrl[2] = round;
+      g.peer.ctrl[3] = 0u;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(g.peer.flag[0]), "r"(round) : "memory");
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(g.peer.flag[1]), "r"(round) : "memory");
+    }
+  }
+}
 
 template <int BN>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t (&v)[32], int row, int col0) {
@@ -129,7 +175,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
 // layout a CU_TENSOR_MAP_SWIZZLE_128B store expects).  `chunk0` = 0 or 4 (first / second 32 columns).
 template <int BN>
 __device__ __forceinline__ void epilogue_stage_half(const GemmArgs& g, const uint32_t (&v)[32], int col0,
-                                                    uint32_t stage_row, int lane, int chunk0) {
+                                                    uint32_t stage_row, int lane, int chunk0,
+                                                    uint16_t* peer_row = nullptr) {
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -168,6 +215,8 @@ __device__ __forceinline__ void epilogue_stage_half(const GemmArgs& g, const uin
     }
     const uint32_t addr = stage_row + (((chunk0 + j) ^ (lane & 7)) << 4);
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+    if (peer_row != nullptr)  // the same 16 bytes straight into the neighbour's halo slot (this lane's row)
+      *reinterpret_cast<uint4*>(peer_row + (chunk0 + j) * 8) = make_uint4(p0, p1, p2, p3);
   }
 }
 
@@ -292,8 +341,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tmem_ld_wait();
           if (lane == 0) tma_store_wait_read<0>();  // previous box of this warp has left the staging buffer
           __syncwarp();
-          epilogue_stage_half<BN>(g, v0, n0 + c, stage_row, lane, 0);
-          epilogue_stage_half<BN>(g, v1, n0 + c + 32, stage_row, lane, 4);
+          uint16_t* const peer_row = peer_row_ptr(g, row, n0 + c);
+          const bool peer_box = g.peer.n_ranges > 0 && __any_sync(0xffffffffu, peer_row != nullptr);
+          epilogue_stage_half<BN>(g, v0, n0 + c, stage_row, lane, 0, peer_row);
+          epilogue_stage_half<BN>(g, v1, n0 + c + 32, stage_row, lane, 4, peer_row);
+          if (peer_box) peer_box_done(g, lane);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -519,8 +571,11 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           tmem_ld_wait();
           if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
-          epilogue_stage_half<BN>(g, v0, n0 + c, stage_row, lane, 0);
-          epilogue_stage_half<BN>(g, v1, n0 + c + 32, stage_row, lane, 4);
+          uint16_t* const peer_row = peer_row_ptr(g, row, n0 + c);
+          const bool peer_box = g.peer.n_ranges > 0 && __any_sync(0xffffffffu, peer_row != nullptr);
+          epilogue_stage_half<BN>(g, v0, n0 + c, stage_row, lane, 0, peer_row);
+          epilogue_stage_half<BN>(g, v1, n0 + c + 32, stage_row, lane, 4, peer_row);
+          if (peer_box) peer_box_done(g, lane);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0 && m0 + q * 32 < g.m) {
@@ -775,8 +830,11 @@ gemm2w_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             if (!live) continue;
             if (lane == 0) tma_store_wait_read<0>();
             __syncwarp();
-            epilogue_stage_half<BN>(g, v0, n0 + c, stage_row, lane, 0);
-            epilogue_stage_half<BN>(g, v1, n0 + c + 32, stage_row, lane, 4);
+            uint16_t* const peer_row = peer_row_ptr(g, row, n0 + c);
+            const bool peer_box = g.peer.n_ranges > 0 && __any_sync(0xffffffffu, peer_row != nullptr);
+            epilogue_stage_half<BN>(g, v0, n0 + c, stage_row, lane, 0, peer_row);
+            epilogue_stage_half<BN>(g, v1, n0 + c + 32, stage_row, lane, 4, peer_row);
+            if (peer_box) peer_box_done(g, lane);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0 && m0 + q * 32 < g.m) {
@@ -886,9 +944,65 @@ extern "C" int ab_gemm_bf16(const AbGemm* p, void* stream) {
              (p->residual == nullptr || p->ldr % 4 == 0) && (p->out_f32 == nullptr || p->ld_f32 % 4 == 0) &&
              (p->out_bf16 == nullptr || p->ld_bf16 % 8 == 0);
 
+  memset(&a.peer, 0, sizeof(a.peer));
   // TMA-store epilogue: 16-bit output only, no residual, 16-byte aligned rows.
   a.tma_out = p->out_bf16 != nullptr && p->out_f32 == nullptr && p->residual == nullptr && al16(p->out_bf16) &&
               p->ld_bf16 % 8 == 0 && (p->bias == nullptr || (reinterpret_cast<uintptr_t>(p->bias) & 15u) == 0);
+  if (p->peer_push != nullptr) {
+    const AbHaloPush* h = p->peer_push;
+    AB_CHECK_ARG(a.tma_out && p->out_dtype == AB_DT_BF16, "ab_gemm_bf16: peer_push needs a 16-bit-only bf16 output");
+    AB_CHECK_ARG(h->c > 0 && 2 * h->c <= 8 && static_cast<long long>(h->c) * h->rows * h->w == p->m &&
+                     h->src_tok_bytes == 2ll * p->n && h->tok_off_bytes % 128 == 0 &&
+                     h->tok_off_bytes + h->tok_bytes == h->src_tok_bytes && h->rows_to_above <= h->rows &&
+                     h->rows_to_below <= h->rows && h->rows_to_above <= h->slot_rows && h->rows_to_below <= h->slot_rows,
+                 "ab_gemm_bf16: peer_push does not describe this output (c=%d rows=%d w=%d, m=%d n=%d)", h->c, h->rows,
+                 h->w, p->m, p->n);
+    PeerRows& pr = a.peer;
+    pr.col_from = static_cast<int>(h->tok_off_bytes / 2);
+    pr.dst_ld = static_cast<int>(h->tok_bytes / 2);
+    pr.flag[0] = h->above_flag;
+    pr.flag[1] = h->below_flag;
+    pr.ctrl = h->ctrl;
+    const long long slot_row_elems = static_cast<long long>(h->w) * pr.dst_ld;
+    for (int c = 0; c < h->c; ++c) {
+      if (h->rows_to_above > 0) {  // my first rows -> rows [0, n) of the slot of the rank above
+        const int i = pr.n_ranges++;
+        pr.row_begin[i] = (c * h->rows) * h->w;
+        pr.row_end[i] = pr.row_begin[i] + h->rows_to_above * h->w;
+        pr.dst[i] = reinterpret_cast<uint16_t*>(h->above_slot) + static_cast<long long>(c) * h->slot_rows * slot_row_elems;
+      }
+      if (h->rows_to_below > 0) {  // my last rows -> rows [slot_rows - n, slot_rows) of the slot of the rank below
+        const int i = pr.n_ranges++;
+        pr.row_begin[i] = (c * h->rows + h->rows - h->rows_to_below) * h->w;
+        pr.row_end[i] = pr.row_begin[i] + h->rows_to_below * h->w;
+        pr.dst[i] = reinterpret_cast<uint16_t*>(h->below_slot) +
+                    (static_cast<long long>(c) * h->slot_rows + h->slot_rows - h->rows_to_below) * slot_row_elems;
+      }
+    }
+    AB_CHECK_ARG(pr.n_ranges > 0, "ab_gemm_bf16: peer_push with nothing to send (use ab_halo_push, which still publishes)");
+    // boxes of this launch that carry peer rows: distinct 32-row groups touched by any range x 64-column boxes sent
+    int groups = 0, last_group = -1;
+    for (int pass = 0; pass < 1; ++pass) {
+      // ranges are emitted in increasing row order per level, and levels increase: a sweep over sorted begins suffices
+      int order[8];
+      for (int i = 0; i < pr.n_ranges; ++i) order[i] = i;
+      for (int i = 1; i < pr.n_ranges; ++i)
+        for (int j = i; j > 0 && pr.row_begin[order[j]] < pr.row_begin[order[j - 1]]; --j) {
+          const int t = order[j];
+          order[j] = order[j - 1];
+          order[j - 1] = t;
+        }
+      for (int k = 0; k < pr.n_ranges; ++k) {
+        const int i = order[k];
+        int g0 = pr.row_begin[i] / 32;
+        const int g1 = (pr.row_end[i] - 1) / 32;
+        if (g0 <= last_group) g0 = last_group + 1;
+        if (g1 >= g0) groups += g1 - g0 + 1;
+        if (g1 > last_group) last_group = g1;
+      }
+    }
+    pr.expected = groups * ((p->n - pr.col_from + 63) / 64);
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   // Large problems run on CTA pairs (cta_group::2); small or narrow ones on the single-CTA kernel.
   static const bool pair_disabled = getenv("AB_GEMM_NO_PAIR") != nullptr;

@@ -112,6 +112,9 @@ class AuroraEngine:
         # double-buffered GEMM followed by the row kernel, because a cluster that owns whole rows fills TMEM with one
         # tile and cannot overlap its HBM-bound epilogue with the next main loop.  AB_FUSE_LN=1 turns it on.
         self.fuse_ln = os.environ.get("AB_FUSE_LN", "0") == "1"
+        # sharded forecast: the QKV projection's epilogue stores the boundary K | V rows into the neighbours' memory itself
+        # (fused compute + exchange, AbGemm.peer_push) instead of a separate copy kernel.  AB_FUSE_PUSH=0 turns it off.
+        self.fuse_push = os.environ.get("AB_FUSE_PUSH", "1") != "0"
         self._shard_plans = None
         # stage-level taps for parity tests: when set to a dict, `_run` stores fp32 copies of the encoder output and
         # of the residual stream after every Swin block / patch merge / patch split under the reference's module names
@@ -662,6 +665,7 @@ class AuroraEngine:
         b.workspace = self._buffer("bb.ws", (nbytes,), torch.uint8).data_ptr()
         b.dim, b.hidden, b.num_heads, b.eps = d, hidden, heads, 1e-5
         b.fuse_ln = int(self.fuse_ln)
+        b.fuse_push = int(self.fuse_push)
         b.window, b.shift = cabi._i3(ws), cabi._i3(ss)
         keep = None
         if slab is None:

@@ -65,6 +65,8 @@ enum { AB_ACT_NONE = 0, AB_ACT_GELU_ERF = 1 };
  * (11-bit mantissa, same tcgen05 rate, saturating stores) to stay closer to it. */
 enum { AB_DT_BF16 = 0, AB_DT_F16 = 1 };
 
+struct AbHaloPush; /* declared below */
+
 typedef struct AbGemm {
   const void* a;       /* bf16 [M, K] */
   const void* w;       /* bf16 [N, K] */
@@ -77,6 +79,11 @@ typedef struct AbGemm {
   int32_t act;
   int32_t in_dtype;    /* AB_DT_*: type of a and w */
   int32_t out_dtype;   /* AB_DT_*: type of the 16-bit output ("out_bf16") */
+  /* Optional fused exchange (latitude-sharded forecast): the epilogue ALSO stores the boundary rows this descriptor
+   * names — columns [tok_off, tok_off + tok_bytes) of the first / last rows of every level of the [C, rows, W, N]
+   * output — straight into the neighbouring GPUs' halo slots over NVLink and publishes the round like ab_halo_push
+   * (which it replaces for this exchange; `local` is ignored).  16-bit-only bf16 output; at least one row to send. */
+  const struct AbHaloPush* peer_push;
 } AbGemm;
 
 int ab_gemm_bf16(const AbGemm* g, void* stream);
@@ -262,6 +269,7 @@ typedef struct AbSwinBlock {
   int32_t slab_h_begin, slab_h_rows, halo_rows;
   float eps;
   int32_t fuse_ln;  /* != 0: adaLN + residual in the epilogue of proj / fc2 (ab_gemm_ln_residual) where dim allows */
+  int32_t fuse_push; /* != 0: the QKV projection's epilogue pushes the halo rows itself (AbGemm.peer_push) */
 } AbSwinBlock;
 
 int ab_swin_block_workspace_bytes(int64_t tokens, int32_t dim, int32_t hidden, size_t* bytes);

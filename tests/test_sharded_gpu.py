@@ -99,7 +99,7 @@ def test_sharded_forward_equals_single_gpu(world, h, w):
     print(f"[sharded x{world}] slabs:", res[0][3][:2], "... max |sharded - single| =", res[0][2], res[0][4])
 
 
-@pytest.mark.parametrize("world,h,w", [(2, 192, 256), (3, 240, 256)])
+@pytest.mark.parametrize("world,h,w", [(2, 192, 256), (3, 240, 256), (8, 640, 256)])
 def test_peer_halo_over_ipc_between_processes_on_one_gpu(world, h, w):
     """The real multi-process protocol on a SINGLE GPU: `world` processes share cuda:0 (the driver time-slices their
     contexts), rendezvous over gloo, map each other's halo buffers with CUDA IPC and run the sharded forward with the
@@ -152,7 +152,7 @@ def test_peer_halo_kernels_on_one_gpu():
 
 def test_sharded_forward_from_pinned_host_memory_uploads_the_band():
     """A batch in PINNED host memory takes the overlapped upload in sharded mode too: only the rank's latitude band goes
-    up, one DMA per (H, W) plane.  World size 1 (band = whole cropped grid, 33 -> 32 rows): same bits as the device path."""
+    up, one DMA per (H, W) plane.  World size 1 (band = whole cropped grid, 193 -> 192 rows): same bits as the device path."""
     import aurora_b200 as ab
     from aurora_b200 import Batch
 
