@@ -182,8 +182,10 @@ def gemm(
     out_f32: Optional[torch.Tensor] = None,
     out_bf16: Optional[torch.Tensor] = None,
     act: int = AB_ACT_NONE,
+    peer_push=None,
 ) -> None:
-    """``out = act(a @ w.T + bias) + residual`` on the tcgen05 GEMM (a, w bf16; outputs preallocated)."""
+    """``out = act(a @ w.T + bias) + residual`` on the tcgen05 GEMM (a, w bf16; outputs preallocated).
+    `peer_push` (an `AbHaloPush`): the epilogue also stores the boundary rows it names into neighbouring GPUs' memory."""
     assert a.dtype == w.dtype, (a.dtype, w.dtype)
     m, k = a.shape
     n, k2 = w.shape
@@ -210,6 +212,8 @@ def gemm(
         g.ld_bf16 = _ld(out_bf16)
         g.out_dtype = _dt(out_bf16)
     g.act = act
+    if peer_push is not None:
+        g.peer_push = C.addressof(peer_push)
     # compulsory HBM bytes: A and W once, every output once, the residual once
     nb = 2.0 * m * k + 2.0 * n * k + m * n * ((4.0 if out_f32 is not None else 0.0) + (2.0 if out_bf16 is not None else 0.0)
                                               + (4.0 if residual is not None else 0.0))

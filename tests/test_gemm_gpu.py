@@ -192,3 +192,49 @@ def test_gemm_ln_residual_rejects_other_widths():
     assert not cabi.gemm_ln_supported(2048) and cabi.gemm_ln_supported(512) and cabi.gemm_ln_supported(1024)
     with pytest.raises(cabi.AbError, match="not supported"):
         cabi.gemm_ln_residual(a, w, out_f32=out)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# fused compute + exchange: the epilogue also stores boundary rows into (peer) halo slots (AbGemm.peer_push)
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", ["single", "pair", "wide"])
+@pytest.mark.parametrize("to_above,to_below", [(3, 2), (0, 5), (1, 0)])
+def test_gemm_epilogue_pushes_boundary_rows_into_halo_slots(variant, to_above, to_below, monkeypatch):
+    """The QKV projection of a latitude band [C, rows, W, 3D] with `peer_push`: columns [D, 3D) of the first `to_above`
+    and last `to_below` rows of every level land in the halo slots (here: in this GPU's own memory) exactly as
+    `ab_halo_push` would place them, the round is published in both flags once, the completion counter is back at zero,
+    and the regular output is untouched by the extra stores.  All three GEMM kernels (single CTA, CTA pair, wide pair)."""
+    from aurora_b200 import cabi
+
+    c, rows, w, d, k, slot_rows = 4, 10, 36, 256, 1024, 5
+    if variant == "single":
+        rows, w = 5, 12          # M = 240 < 1024: single-CTA kernel
+        to_above, to_below = min(to_above, rows), min(to_below, rows)
+    monkeypatch.setenv("AB_GEMM_WIDE", "2" if variant == "wide" else "0")
+    m, n = c * rows * w, 3 * d
+    torch.manual_seed(c + rows + w + to_above)
+    dev = "cuda"
+    a = torch.randn(m, k, device=dev).to(torch.bfloat16)
+    wt = (torch.randn(n, k, device=dev) / k**0.5).to(torch.bfloat16)
+    bias = torch.randn(n, device=dev)
+    ref_out = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
+    cabi.gemm(a, wt, bias=bias, out_bf16=ref_out)
+    out = torch.full((m, n), float("nan"), device=dev, dtype=torch.bfloat16)
+    slots = torch.full((2, c, slot_rows, w, 2 * d), float("nan"), device=dev, dtype=torch.bfloat16)
+    ctrl = torch.zeros(64, device=dev, dtype=torch.int32)
+    ctrl[2] = 41  # the previous round
+    hp = cabi.AbHaloPush()
+    hp.above_slot, hp.below_slot = slots[1].data_ptr(), slots[0].data_ptr()   # side 1 of the rank above, side 0 of the rank below
+    hp.above_flag, hp.below_flag, hp.ctrl = ctrl.data_ptr() + 4, ctrl.data_ptr(), ctrl.data_ptr()
+    hp.c, hp.rows, hp.w, hp.slot_rows = c, rows, w, slot_rows
+    hp.rows_to_above, hp.rows_to_below = to_above, to_below
+    hp.src_tok_bytes, hp.tok_off_bytes, hp.tok_bytes = 3 * d * 2, d * 2, 2 * d * 2
+    cabi.gemm(a, wt, bias=bias, out_bf16=out, peer_push=hp)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref_out)
+    assert ctrl[:4].tolist() == [42, 42, 42, 0]
+    o4 = ref_out.view(c, rows, w, n)[..., d:]
+    assert torch.equal(slots[1][:, :to_above], o4[:, :to_above])                                 # my first rows -> above
+    assert torch.isnan(slots[1][:, to_above:].float()).all()
+    assert torch.equal(slots[0][:, slot_rows - to_below:], o4[:, rows - to_below:])             # my last rows -> below
+    assert torch.isnan(slots[0][:, : slot_rows - to_below].float()).all()
