@@ -112,9 +112,12 @@ class AuroraEngine:
         # double-buffered GEMM followed by the row kernel, because a cluster that owns whole rows fills TMEM with one
         # tile and cannot overlap its HBM-bound epilogue with the next main loop.  AB_FUSE_LN=1 turns it on.
         self.fuse_ln = os.environ.get("AB_FUSE_LN", "0") == "1"
-        # sharded forecast: the QKV projection's epilogue stores the boundary K | V rows into the neighbours' memory itself
-        # (fused compute + exchange, AbGemm.peer_push) instead of a separate copy kernel.  AB_FUSE_PUSH=0 turns it off.
-        self.fuse_push = os.environ.get("AB_FUSE_PUSH", "1") != "0"
+        # sharded forecast: the QKV projection's epilogue can store the boundary K | V rows into the neighbours' memory itself
+        # (fused compute + exchange, AbGemm.peer_push) instead of the copy kernel.  Bit-identical, but measured 4 % SLOWER
+        # per step at 4 GPUs (35.6 vs 34.2 ms, profiles/r02_kernel_probes.md): the epilogue's per-lane 16-byte stores make
+        # small NVLink packets and stall the epilogue warps, while the copy kernel keeps 2 CTAs per SM of wide stores in
+        # flight.  OFF by default; AB_FUSE_PUSH=1 turns it on.
+        self.fuse_push = os.environ.get("AB_FUSE_PUSH", "0") == "1"
         self._shard_plans = None
         # stage-level taps for parity tests: when set to a dict, `_run` stores fp32 copies of the encoder output and
         # of the residual stream after every Swin block / patch merge / patch split under the reference's module names

@@ -438,7 +438,9 @@ def run_reference_arm(args) -> None:
         # wall time of one timed (bounded-sample) step; a whole forecast step is `sample_scale` times that
         "ms_per_step": 1000.0 * sum(times) / len(times), "ms_per_whole_step": 1000.0 / v,
         "sample_scale": m.get("sample_scale"),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True,
+        "scaling": "strong" if resolve_parallelism(args.workload, args.gpus, args.parallelism) == "latshard" else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.workload, args.gpus, args.parallelism),
         "cpu_baseline": m,
         "e2e": {"value": v, "unit": "forecast-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

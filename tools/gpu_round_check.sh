@@ -1,6 +1,6 @@
 #!/bin/bash
 # One gpurun call that re-validates the tree on a B200; everything lands in gpurun_out/.  Sections (pick with $1,
-# default "smoke tests bench"): smoke | tests | bench | refarm | probe | ncu
+# default "smoke tests bench"): smoke | tests | bench | graph | refarm | ncu | ncufull
 mkdir -p gpurun_out
 SECTIONS="${*:-smoke tests bench}"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/gpu.txt 2>&1
@@ -29,9 +29,6 @@ E
 refarm)
   ( time timeout 1200 python bench.py --impl reference --steps 4 --warmup 1 ) > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "refarm rc=$?"
   cut -c1-1200 gpurun_out/bench_ref.json ;;
-probe)
-  ( time timeout 300 python experimental/probe_attn_x1.py ) > gpurun_out/probe_attn_x1.log 2>&1; echo "probe rc=$?"
-  tail -12 gpurun_out/probe_attn_x1.log | cut -c1-400 ;;
 graph)
   ( time timeout 400 python bench.py --steps 10 --warmup 3 --cuda-graph --rollout 40 --no-cpu-baseline --no-gpu-reference ) > gpurun_out/bench_graph.json 2> gpurun_out/bench_graph.err; echo "graph rc=$?"
   python tools/show_bench.py gpurun_out/bench_graph.json ;;
