@@ -570,7 +570,9 @@ def main() -> None:
             for p in ab.rollout(model, host_batch, steps=n):   # initial H2D inside; the caller keeps only the last step
                 last = p
             return last
-        run_rollout(2)
+        # warm-up: steps 0, 1 and >= 2 have different graph signatures (the positive-variable clamp starts at step 2,
+        # `from_second` LoRA at step 1): three steps capture every graph a long roll-out replays
+        run_rollout(min(args.rollout, 3))
         barrier()
         e0.record()
         run_rollout(args.rollout)
