@@ -651,8 +651,10 @@ def main() -> None:
             "bound": "nvlink", "exchanges_per_step": n_hp, "push_seconds_per_step": t_hp,
             "push_achieved_gbs": b_hp / t_hp / 1e9 if t_hp else None, "nvlink_peak_gbs_per_direction": 900.0,
             "bytes_sent_per_exchange": b_hp / n_hp, "wait_seconds_per_step": t_hw,
-            "note": "rank 0, one eager instrumented step: push = stores into both neighbours' memory over NVLink; wait = "
-                    "spinning until both neighbours' pushes landed (includes the ranks' skew)"}
+            "note": "rank 0, one eager instrumented step: push = stores into both neighbours' memory over NVLink; the wait "
+                    "for the neighbours' rows happens inside the attention kernel (its loaders spin on the flags before the "
+                    "first foreign row), so it is part of window_attention's time; wait_seconds_per_step is the stand-alone "
+                    "wait kernel, no longer launched"}
 
     # ---- max over ranks (times); bytes moved are summed over ranks for a sharded forecast ----
     if distributed:
