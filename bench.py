@@ -544,12 +544,22 @@ def main() -> None:
     # ---- end to end through the public API from pinned host memory ----
     e2e_ms = None
     if not args.no_e2e:
+        d2h_stream = torch.cuda.Stream(device=dev)
+
         def e2e_step():
             p = model.forward(host_batch)     # the public call on HOST tensors: H2D of every field happens inside
                                               # (pinned source -> copy stream, overlaps the previous step's kernels)
-            for grp in (p.surf_vars, p.atmos_vars):
-                for k, v in grp.items():
-                    host_out[k].copy_(v, non_blocking=True)   # D2H of the whole prediction
+            # D2H of the whole prediction into pinned host buffers, like a consumer that streams results out: on its own
+            # stream behind an event, so that the read-back of step n runs under the kernels of step n + 1 (the
+            # predictions are fresh tensors every step; record_stream keeps the allocator from recycling them early)
+            done = torch.cuda.Event()
+            done.record()
+            d2h_stream.wait_event(done)
+            with torch.cuda.stream(d2h_stream):
+                for grp in (p.surf_vars, p.atmos_vars):
+                    for k, v in grp.items():
+                        host_out[k].copy_(v, non_blocking=True)
+                        v.record_stream(d2h_stream)
             return p
         e2e_step()
         barrier()
