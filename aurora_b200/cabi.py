@@ -114,6 +114,7 @@ EXPORTS = [
     "ab_swin_block_workspace_bytes",
     "ab_gemm_ln_supported",
     "ab_gemm_ln_residual",
+    "ab_run_ops",
 ]
 AB_IPC_HANDLE_BYTES = 64
 AB_HALO_CTRL_BYTES = 256
@@ -125,6 +126,12 @@ AB_IN_NAN_TO_ZERO, AB_IN_DENSITY, AB_IN_SIN_DEG, AB_IN_COS_DEG = 3, 4, 5, 6
 # Optional per-call device timing (bench.py's roofline leg): when PROFILE is a dict, every op wrapper
 # records a CUDA-event pair on the current stream under its kernel name.
 PROFILE: Optional[dict] = None
+
+# Plan recording: when RECORD is a list, the wrappers that `ab_run_ops` can replay (gemm, swin_block, ln_mod_residual,
+# patch_merge_ln, patch_split_ln) append their filled descriptor as (AB_OP_* kind, struct) INSTEAD of launching; the
+# caller turns the list into an `AbOp` array with `make_program` and replays it with `run_ops` (one C call).
+RECORD: Optional[list] = None
+AB_OP_GEMM, AB_OP_SWIN_BLOCK, AB_OP_LN_MOD_RESIDUAL, AB_OP_PATCH_MERGE_LN, AB_OP_PATCH_SPLIT_LN = 1, 2, 3, 4, 5
 
 
 class _Timed:
@@ -217,6 +224,9 @@ def gemm(
     # compulsory HBM bytes: A and W once, every output once, the residual once
     nb = 2.0 * m * k + 2.0 * n * k + m * n * ((4.0 if out_f32 is not None else 0.0) + (2.0 if out_bf16 is not None else 0.0)
                                               + (4.0 if residual is not None else 0.0))
+    if RECORD is not None:
+        RECORD.append((AB_OP_GEMM, g))
+        return
     with _Timed("gemm", work=2.0 * m * n * k, nbytes=nb):
         check(lib().ab_gemm_bf16(C.byref(g), C.c_void_p(stream_ptr())), "ab_gemm_bf16")
 
@@ -265,6 +275,18 @@ class AbLnModResidual(C.Structure):
         ("in_dtype", C.c_int32),
         ("out_dtype", C.c_int32),
     ]
+
+
+class AbPatchMergeLn(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("out_bf16", C.c_void_p),
+                ("batch", C.c_int32), ("c", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("d", C.c_int32),
+                ("eps", C.c_float)]
+
+
+class AbPatchSplitLn(C.Structure):
+    _fields_ = [("y_bf16", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("out_bf16", C.c_void_p),
+                ("batch", C.c_int32), ("c", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("d", C.c_int32),
+                ("crop_h", C.c_int32), ("crop_w", C.c_int32), ("eps", C.c_float)]
 
 
 class AbFieldIn(C.Structure):
@@ -409,6 +431,9 @@ def ln_mod_residual(y: torch.Tensor, *, scale=None, shift=None, residual=None, a
     nb = rows * dim * (2.0 + (4.0 if residual is not None and res_mod == 0 else 0.0)
                        + (4.0 if out_f32 is not None else 0.0) + (2.0 if out_bf16 is not None else 0.0)
                        + (4.0 if add_rows is not None else 0.0))
+    if RECORD is not None:
+        RECORD.append((AB_OP_LN_MOD_RESIDUAL, a))
+        return
     with _Timed("ln_mod_residual", nbytes=nb):
         check(lib().ab_ln_mod_residual(C.byref(a), _s()), "ab_ln_mod_residual")
 
@@ -417,6 +442,10 @@ def patch_merge_ln(x: torch.Tensor, gamma, beta, out: torch.Tensor, *, batch, c,
     assert x.dtype == torch.float32 and x.is_contiguous() and x.numel() == batch * c * h * w * d
     assert out.dtype == torch.bfloat16 and out.is_contiguous()
     assert out.numel() == batch * c * ((h + 1) // 2) * ((w + 1) // 2) * 4 * d
+    if RECORD is not None:
+        m = AbPatchMergeLn(x=ptr(x), gamma=ptr(gamma), beta=ptr(beta), out_bf16=ptr(out), batch=batch, c=c, h=h, w=w, d=d, eps=eps)
+        RECORD.append((AB_OP_PATCH_MERGE_LN, m))
+        return
     check(lib().ab_patch_merge_ln(C.c_void_p(ptr(x)), C.c_void_p(ptr(gamma)), C.c_void_p(ptr(beta)),
                                   C.c_void_p(ptr(out)), batch, c, h, w, d, C.c_float(eps), _s()), "ab_patch_merge_ln")
 
@@ -426,6 +455,11 @@ def patch_split_ln(y: torch.Tensor, gamma, beta, out: torch.Tensor, *, batch, c,
     assert y.dtype == torch.bfloat16 and y.is_contiguous() and y.numel() == batch * c * h * w * 2 * d
     assert out.dtype == torch.bfloat16 and out.is_contiguous()
     assert out.numel() == batch * c * (2 * h - crop_h) * (2 * w - crop_w) * (d // 2)
+    if RECORD is not None:
+        sp = AbPatchSplitLn(y_bf16=ptr(y), gamma=ptr(gamma), beta=ptr(beta), out_bf16=ptr(out), batch=batch, c=c, h=h, w=w,
+                            d=d, crop_h=crop_h, crop_w=crop_w, eps=eps)
+        RECORD.append((AB_OP_PATCH_SPLIT_LN, sp))
+        return
     check(lib().ab_patch_split_ln(C.c_void_p(ptr(y)), C.c_void_p(ptr(gamma)), C.c_void_p(ptr(beta)),
                                   C.c_void_p(ptr(out)), batch, c, h, w, d, crop_h, crop_w, C.c_float(eps), _s()),
           "ab_patch_split_ln")
@@ -561,6 +595,9 @@ def swin_block_workspace_bytes(tokens: int, dim: int, hidden: int) -> int:
 
 def swin_block(desc: AbSwinBlock) -> None:
     """One whole Swin3DTransformerBlock in place on the token stream (see include/aurora_b200.h)."""
+    if RECORD is not None:
+        RECORD.append((AB_OP_SWIN_BLOCK, desc))
+        return
     check(lib().ab_swin_block(C.byref(desc), _s()), "ab_swin_block")
 
 
@@ -606,3 +643,30 @@ def gemm_ln_residual(a: torch.Tensor, w: torch.Tensor, *, bias=None, scale=None,
                                               + (2.0 if out_bf16 is not None else 0.0))
     with _Timed("gemm_ln", work=2.0 * m * n * k, nbytes=nb):
         check(lib().ab_gemm_ln_residual(C.byref(g), _s()), "ab_gemm_ln_residual")
+
+
+# ---- whole-stage replay (ab_run_ops) ------------------------------------------------------------------------------
+class _AbOpUnion(C.Union):
+    _fields_ = [("gemm", AbGemm), ("block", AbSwinBlock), ("ln", AbLnModResidual), ("merge", AbPatchMergeLn),
+                ("split", AbPatchSplitLn)]
+
+
+class AbOp(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved_", C.c_int32), ("u", _AbOpUnion)]
+
+
+_OP_FIELD = {AB_OP_GEMM: "gemm", AB_OP_SWIN_BLOCK: "block", AB_OP_LN_MOD_RESIDUAL: "ln", AB_OP_PATCH_MERGE_LN: "merge",
+             AB_OP_PATCH_SPLIT_LN: "split"}
+
+
+def make_program(recorded: list):
+    """`recorded` = [(AB_OP_* kind, descriptor struct), ...] as collected under RECORD -> (AbOp array, keep-alive list)."""
+    arr = (AbOp * len(recorded))()
+    for i, (kind, desc) in enumerate(recorded):
+        arr[i].kind = kind
+        setattr(arr[i].u, _OP_FIELD[kind], desc)   # copies the struct; pointers inside keep pointing at caller-owned memory
+    return arr, [d for _, d in recorded]
+
+
+def run_ops(program) -> None:
+    check(lib().ab_run_ops(program, len(program), _s()), "ab_run_ops")

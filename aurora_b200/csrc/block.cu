@@ -144,3 +144,39 @@ extern "C" int ab_swin_block(const AbSwinBlock* b, void* stream) {
   }
   return ab_ln_mod_residual(&ln, stream);
 }
+
+extern "C" int ab_run_ops(const AbOp* ops, int32_t n_ops, void* stream) {
+  using namespace ab;
+  AB_CHECK_ARG(ops != nullptr && n_ops >= 0, "ab_run_ops: null list");
+  for (int i = 0; i < n_ops; ++i) {
+    const AbOp& op = ops[i];
+    int rc;
+    switch (op.kind) {
+      case AB_OP_GEMM:
+        rc = ab_gemm_bf16(&op.u.gemm, stream);
+        break;
+      case AB_OP_SWIN_BLOCK:
+        rc = ab_swin_block(&op.u.block, stream);
+        break;
+      case AB_OP_LN_MOD_RESIDUAL:
+        rc = ab_ln_mod_residual(&op.u.ln, stream);
+        break;
+      case AB_OP_PATCH_MERGE_LN: {
+        const AbPatchMergeLn& m = op.u.merge;
+        rc = ab_patch_merge_ln(m.x, m.gamma, m.beta, m.out_bf16, m.batch, m.c, m.h, m.w, m.d, m.eps, stream);
+        break;
+      }
+      case AB_OP_PATCH_SPLIT_LN: {
+        const AbPatchSplitLn& sp = op.u.split;
+        rc = ab_patch_split_ln(sp.y_bf16, sp.gamma, sp.beta, sp.out_bf16, sp.batch, sp.c, sp.h, sp.w, sp.d, sp.crop_h,
+                               sp.crop_w, sp.eps, stream);
+        break;
+      }
+      default:
+        set_error("ab_run_ops: unknown operation kind %d at index %d", op.kind, i);
+        return AB_ERR_INVALID_ARGUMENT;
+    }
+    if (rc != AB_OK) return rc;  // ab_last_error() describes the failing operation
+  }
+  return AB_OK;
+}

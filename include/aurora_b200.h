@@ -304,6 +304,33 @@ typedef struct AbGemmLn {
 int ab_gemm_ln_supported(int32_t n);
 int ab_gemm_ln_residual(const AbGemmLn* p, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * A whole stage in ONE call: ab_run_ops executes a caller-built list of operations in order on `stream` — e.g. the
+ * complete Swin3DTransformerBackbone (swin3d.py:884-936: 48 AB_OP_SWIN_BLOCK + patch merges / splits with their
+ * projections), which the engine records once per input signature and then replays with one call per step.  The list
+ * is plain host memory owned by the caller (the "plan": it bakes device pointers, so it stays valid as long as the
+ * buffers it names do); the library keeps nothing.  Stops at the first failing operation and returns its status.
+ * ---------------------------------------------------------------------------------------------- */
+enum { AB_OP_GEMM = 1, AB_OP_SWIN_BLOCK = 2, AB_OP_LN_MOD_RESIDUAL = 3, AB_OP_PATCH_MERGE_LN = 4, AB_OP_PATCH_SPLIT_LN = 5 };
+
+typedef struct AbPatchMergeLn { /* arguments of ab_patch_merge_ln */
+  const float* x;
+  const float* gamma;
+  const float* beta;
+  void* out_bf16;
+  int32_t batch, c, h, w, d;
+  float eps;
+} AbPatchMergeLn;
+
+typedef struct AbPatchSplitLn { /* arguments of ab_patch_split_ln */
+  const void* y_bf16;
+  const float* gamma;
+  const float* beta;
+  void* out_bf16;
+  int32_t batch, c, h, w, d, crop_h, crop_w;
+  float eps;
+} AbPatchSplitLn;
+
 /* PatchMerging3D front half (swin3d.py:526-553): x f32 [batch, C, H, W, D] -> zero pad H, W to even at
  * the bottom / right -> 2x2 gather with feature order (h w D) -> LayerNorm(4D) with affine gamma/beta
  * -> bf16 [batch*C*ceil(H/2)*ceil(W/2), 4D], the A operand of `reduction` (ab_gemm_bf16). */
@@ -383,6 +410,20 @@ typedef struct AbFieldOut {
  * unpatchify (decoder.py:214-217,250-263; util.py:18-41), the post-decoder hooks and Batch.unnormalise. */
 int ab_unpatchify(const AbFieldOut* fields, int32_t nfields, const float* y, int32_t ldy, int32_t h, int32_t w,
                   int32_t p, void* stream);
+
+typedef struct AbOp {
+  int32_t kind; /* AB_OP_* */
+  int32_t reserved_;
+  union {
+    AbGemm gemm;
+    AbSwinBlock block;
+    AbLnModResidual ln;
+    AbPatchMergeLn merge;
+    AbPatchSplitLn split;
+  } u;
+} AbOp;
+
+int ab_run_ops(const AbOp* ops, int32_t n_ops, void* stream);
 
 #ifdef __cplusplus
 }

@@ -287,6 +287,23 @@ def test_whole_block_entry_point_equals_the_per_kernel_path():
         assert torch.equal(plain.atmos_vars[k], fused.atmos_vars[k]), k
     for k in plain.surf_vars:
         assert torch.equal(plain.surf_vars[k], fused.surf_vars[k]), k
+    # ... and the whole backbone replayed from its recorded operation list (ONE ab_run_ops call per step) against
+    # one ab_swin_block call per block: the forward above used the plan (eng.use_program), now without it
+    assert eng.use_program and len(eng._programs) == 1
+    eng.block_entry, eng.use_program = True, False
+    n0 = cabi.launch_count()
+    per_block = model.forward(batch)
+    assert cabi.launch_count() - n0 == n_plain
+    for k in plain.atmos_vars:
+        assert torch.equal(per_block.atmos_vars[k], fused.atmos_vars[k]), k
+    # the plan follows new inputs (it bakes buffer addresses, not values) and other roll-out steps get their own plan
+    eng.use_program = True
+    b2 = fx.make_batch(cfg, 192, 256, levels=fx.LEVELS4, b=1, seed=30, rollout_step=1)
+    with_plan = {k: v.clone() for k, v in model.forward(b2).atmos_vars.items()}
+    eng.use_program = False
+    without = model.forward(b2).atmos_vars
+    for k in with_plan:
+        assert torch.equal(with_plan[k], without[k]), k
 
 
 def test_stage_seams_backbone_forward_and_hooks():
