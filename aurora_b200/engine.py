@@ -107,7 +107,8 @@ class AuroraEngine:
         self._peer: Optional["sharding.PeerHalo"] = None
         self._slab_cache: dict = {}
         self.block_entry = True  # run Swin blocks through the whole-block entry point ab_swin_block
-        self.use_program = True  # replay the whole backbone from a recorded AbOp list with one ab_run_ops call
+        # replay the whole backbone from a recorded AbOp list with one ab_run_ops call (AB_USE_PROGRAM=0: one call per block)
+        self.use_program = os.environ.get("AB_USE_PROGRAM", "1") != "0"
         self._programs: dict = {}
         # adaLN + residual fused into the epilogue of proj / fc2 (ab_gemm_ln_residual, D = 512 / 1024).  OFF by default:
         # measured on B200 (profiles/r02_kernel_probes.md) the fused kernel is correct but 3 - 60 % SLOWER than the
