@@ -115,6 +115,7 @@ EXPORTS = [
     "ab_gemm_ln_supported",
     "ab_gemm_ln_residual",
     "ab_run_ops",
+    "ab_struct_size",
 ]
 AB_IPC_HANDLE_BYTES = 64
 AB_HALO_CTRL_BYTES = 256

@@ -180,3 +180,20 @@ extern "C" int ab_run_ops(const AbOp* ops, int32_t n_ops, void* stream) {
   }
   return AB_OK;
 }
+
+extern "C" int ab_struct_size(int32_t which) {
+  switch (which) {
+    case 0: return static_cast<int>(sizeof(AbGemm));
+    case 1: return static_cast<int>(sizeof(AbWindowAttention));
+    case 2: return static_cast<int>(sizeof(AbLnModResidual));
+    case 3: return static_cast<int>(sizeof(AbFieldIn));
+    case 4: return static_cast<int>(sizeof(AbFieldOut));
+    case 5: return static_cast<int>(sizeof(AbHaloPush));
+    case 6: return static_cast<int>(sizeof(AbSwinBlock));
+    case 7: return static_cast<int>(sizeof(AbGemmLn));
+    case 8: return static_cast<int>(sizeof(AbPatchMergeLn));
+    case 9: return static_cast<int>(sizeof(AbPatchSplitLn));
+    case 10: return static_cast<int>(sizeof(AbOp));
+    default: return -1;
+  }
+}

@@ -425,6 +425,11 @@ typedef struct AbOp {
 
 int ab_run_ops(const AbOp* ops, int32_t n_ops, void* stream);
 
+/* sizeof() of the descriptor structs as this library was compiled (binding authors: compare with your mirror).
+ * which: 0 AbGemm, 1 AbWindowAttention, 2 AbLnModResidual, 3 AbFieldIn, 4 AbFieldOut, 5 AbHaloPush, 6 AbSwinBlock,
+ * 7 AbGemmLn, 8 AbPatchMergeLn, 9 AbPatchSplitLn, 10 AbOp; -1 for an unknown index.  Host only. */
+int ab_struct_size(int32_t which);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,3 +73,23 @@ def test_host_index_map_production_checksums():
         idx, grp = cabi.window_index_map_host(res, WS0, ss0, True)
         got = idx if kind == "idx" else grp
         assert hashlib.sha256(got.tobytes()).hexdigest() == want, key
+
+
+def test_ctypes_mirrors_have_the_library_struct_sizes():
+    """Every descriptor struct is mirrored by hand in aurora_b200/cabi.py: its size must equal sizeof() as the library
+    was compiled (catches a field added on one side only, or a padding difference)."""
+    lib = cabi.lib()
+    mirrors = [cabi.AbGemm, cabi.AbWindowAttention, cabi.AbLnModResidual, cabi.AbFieldIn, cabi.AbFieldOut, cabi.AbHaloPush,
+               cabi.AbSwinBlock, cabi.AbGemmLn, cabi.AbPatchMergeLn, cabi.AbPatchSplitLn, cabi.AbOp]
+    for which, struct in enumerate(mirrors):
+        assert lib.ab_struct_size(which) == C.sizeof(struct), (struct.__name__, lib.ab_struct_size(which), C.sizeof(struct))
+    assert lib.ab_struct_size(len(mirrors)) == -1
+
+
+def test_run_ops_validates_without_a_gpu():
+    lib = cabi.lib()
+    assert lib.ab_run_ops(None, 0, None) == -1
+    ops = (cabi.AbOp * 1)()
+    ops[0].kind = 99
+    assert lib.ab_run_ops(ops, 1, None) == -1 and b"unknown operation kind 99" in lib.ab_last_error()
+    assert lib.ab_run_ops(ops, 0, None) == 0   # an empty list is a no-op
