@@ -61,6 +61,12 @@ def _worker(rank, world, port, q):
     top = [(rank * rows - halo + i) % h for i in range(halo)]
     bot = [((rank + 1) * rows + i) % h for i in range(halo)]
     ok = torch.equal(got[0], full[:, top]) and torch.equal(got[1], full[:, bot])
+    # the K | V form the engine uses: a [C, rows, W, 3D] projection, of which only columns [D, 3D) are exchanged
+    w_tok, d = 4, 2
+    full4 = torch.randn(c, h, w_tok, 3 * d)
+    got4 = S.exchange_halo(full4[:, rank * rows:(rank + 1) * rows].contiguous(), halo, col_from=d)
+    ok = ok and got4.shape == (2, c, halo, w_tok, 2 * d)
+    ok = ok and torch.equal(got4[0], full4[:, top][..., d:]) and torch.equal(got4[1], full4[:, bot][..., d:])
     q.put((rank, bool(ok)))
     dist.barrier()
     dist.destroy_process_group()
