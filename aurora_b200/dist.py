@@ -1,7 +1,7 @@
-"""Multi-GPU plumbing for replica runs: one process per GPU, `torch.distributed` for rendezvous and for
-the only cross-rank operations the forward path needs today — a barrier and a max-reduction of device
-timings.  Independent forecasts need no data-path collective; the latitude sharding of a
-single forecast and its halo exchange live in `aurora_b200/sharding.py`."""
+"""Multi-GPU plumbing shared by both parallel modes: one process per GPU, `torch.distributed` for rendezvous, a barrier
+and a max-reduction of device timings.  Independent forecasts (replicas) need no data-path collective; the latitude
+sharding of ONE forecast — the default of `bench.py --gpus N` — and its peer-memory / NCCL halo exchange live in
+`aurora_b200/sharding.py` and `csrc/halo.cu`."""
 
 from __future__ import annotations
 
